@@ -1,0 +1,109 @@
+/* optdyn_b200 — C ABI of the B200 optimization-based-dynamics hot path.
+ *
+ * Drop-in boundary for the inner loop the reference (thowell/optimization_dynamics) exposes to IterativeLQR:
+ *     f / fx / fu                      reference src/dynamics.jl:81-128
+ *     fx_gb / fu_gb (gradient bundle)  reference src/gradient_bundle.jl:87-147, src/ls.jl:44-60
+ *     f/fx/fu_rocket[_proj]            reference src/models/rocket/dynamics.jl:101-269
+ * Every entry point is batched: B independent (timestep × sample × rollout) problems per call.  Plain C types only; the
+ * Julia `ccall` / Python `ctypes` bindings are shown in INTEGRATION.md.  All real data is IEEE fp64.
+ *
+ * Array conventions
+ *   q1, q2 : B×nq, u : B×nu, row per problem (x = [q1; q2] of the reference, src/dynamics.jl:82-83).
+ *   q3     : B×nq.
+ *   dq3dq1, dq3dq2 : B×(nq×nq), dq3du1 : B×(nq×nu) — each block COLUMN-major (Julia layout), i.e. exactly
+ *            grad_sim.grad.∂q3∂q1[1], ∂q3∂q2[1], ∂q3∂u1[1] of src/dynamics.jl:110-111,125.
+ *   packed : in  row = [q1 | q2 | u]                         (2nq+nu doubles)
+ *            out row = [q3 | ∂q3/∂q1 | ∂q3/∂q2 | ∂q3/∂u1]    (nq + nq(2nq+nu) doubles; hopper: 44 = 352 B)
+ *   status : int32 per problem, 0 = both solves converged.  Low nibble = eval solve (f), next nibble = gradient solve
+ *            (fx/fu): 1 = iteration cap (max_iter), 2 = non-finite iterate or singular Jacobian.  The reference ignores the
+ *            solver status (src/dynamics.jl:88); callers of this ABI should not.
+ *   iters  : int32 per problem, eval iterations | gradient iterations << 16 (may be NULL).
+ * "_device" entry points take device pointers, enqueue on the handle's stream and return without synchronising.
+ * The others take host pointers (pinned or pageable), copy H2D/D2H on the handle's stream and synchronise before returning.
+ * Return value: 0 on success, non-zero on error (message via od_last_error()).  There is no CPU fallback.
+ */
+#ifndef OPTDYN_B200_H
+#define OPTDYN_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum od_model {
+    OD_ACROBOT_IMPACT = 0,        /* reference src/models/acrobot/model.jl:121-142  */
+    OD_ACROBOT_NOMINAL = 1,       /* reference src/models/acrobot/model.jl:144-157  */
+    OD_CARTPOLE_FRICTION = 2,     /* reference src/models/cartpole/model.jl:81-114  */
+    OD_CARTPOLE_FRICTIONLESS = 3, /* reference src/models/cartpole/model.jl:116-129 */
+    OD_PLANAR_PUSH = 4,           /* reference src/models/planar_push/model.jl:121-187 */
+    OD_HOPPER = 5,                /* RoboDojo.hopper, reference examples/hopper.jl:14,38-50 */
+    OD_ROCKET = 6                 /* reference src/models/rocket/codegen.jl:14-22,45-64 */
+};
+
+/* InteriorPointOptions as the reference sets them (src/dynamics.jl:25-33; rocket: src/models/rocket/dynamics.jl:21-27,77-86). */
+typedef struct od_options {
+    double r_tol;          /* 1e-8 */
+    double kappa_eval_tol; /* κ_eval_tol, e.g. 1e-4 (examples/hopper.jl:42) */
+    double kappa_grad_tol; /* κ_grad_tol, e.g. 1e-3 */
+    double ls_scale;       /* 0.5 */
+    int32_t max_iter;      /* 100 */
+    int32_t max_ls;        /* 25 */
+} od_options;
+
+typedef struct od_handle od_handle;
+
+/* Fills *opts with the reference's settings for `model`. */
+int od_default_options(int model, od_options* opts);
+/* nq, nu, nz (decision variables), ntheta (data vector) of a model; any pointer may be NULL. */
+int od_model_dims(int model, int* nq, int* nu, int* nz, int* ntheta);
+
+/* ImplicitDynamics(model, h, …; r_tol, κ_eval_tol, κ_grad_tol) — reference src/dynamics.jl:51-79.
+ * params: friction coefficients for OD_CARTPOLE_FRICTION [μ_slider, μ_angle] and OD_HOPPER [μ_body, μ_foot] (the reference
+ * mutates model.friction after construction, examples/cartpole.jl:21), u_max for OD_ROCKET; NULL/0 = model defaults.
+ * device: CUDA device ordinal.  Returns NULL on failure. */
+od_handle* od_create(int model, double h, const od_options* opts, const double* params, int nparams, int device);
+void od_destroy(od_handle* hd);
+/* Use an existing cudaStream_t (e.g. the caller's framework stream) instead of the handle's own stream. */
+int od_set_stream(od_handle* hd, void* cuda_stream);
+int od_synchronize(od_handle* hd);
+
+/* f for a batch: q3 = step!(eval_sim, q2, (q2−q1)/h, u)  — reference src/dynamics.jl:81-94.  Host pointers. */
+int od_step_batch(od_handle* hd, int B, const double* q1, const double* q2, const double* u, double* q3, int32_t* status);
+/* f + fx + fu for a batch with the duplicate gradient solve removed — reference src/dynamics.jl:81-128.  Host pointers;
+ * q3 may be NULL (fx/fu only). */
+int od_step_grad_batch(od_handle* hd, int B, const double* q1, const double* q2, const double* u,
+                       double* q3, double* dq3dq1, double* dq3dq2, double* dq3du1, int32_t* status);
+/* Same, one packed host row per problem in and out (fewest transfers: 1 H2D, 2 D2H). */
+int od_step_grad_packed(od_handle* hd, int B, const double* in, double* out, int32_t* status);
+
+/* Device-pointer variants (asynchronous).  want_eval / want_grad select f and/or fx+fu. */
+int od_step_grad_batch_device(od_handle* hd, int B, const double* q1, const double* q2, const double* u,
+                              double* q3, double* dq3dq1, double* dq3dq2, double* dq3du1, int32_t* status, int32_t* iters,
+                              int want_eval, int want_grad);
+int od_step_grad_packed_device(od_handle* hd, int B, const double* in, double* out, int32_t* status, int32_t* iters,
+                               int want_eval, int want_grad);
+
+/* Gradient bundle — gradient!(eval_sim, gb, q1, q2, u1), reference src/gradient_bundle.jl:87-104: one nominal and N perturbed
+ * eval-sim steps per problem ((N+1)·B solves in one launch), then the least-squares fit of src/ls.jl:44-60 in closed form
+ * (normal equations).  eta: N×(2nq+nu) perturbations shared by the batch (host).  dz: B×(nq×(2nq+nu)) column-major (host).
+ * status: OR of the statuses of the N+1 solves; 8 = singular normal equations (a coordinate never perturbed). */
+int od_bundle_batch(od_handle* hd, int B, int N, const double* eta, const double* q1, const double* q2, const double* u,
+                    double* dz, int32_t* status);
+
+/* Rocket: f/fx/fu_rocket (proj = 0) and f/fx/fu_rocket_proj (proj = 1) — reference src/models/rocket/dynamics.jl:101-269.
+ * x: B×12, u: B×3 → y: B×12, dx: B×(12×12), du: B×(12×3) column-major; dx/du may be NULL (f only).  Host pointers.
+ * status low nibble = dynamics solve, next nibble = projection solve. */
+int od_rocket_batch(od_handle* hd, int B, const double* x, const double* u, int proj, double* y, double* dx, double* du, int32_t* status);
+int od_rocket_batch_device(od_handle* hd, int B, const double* x, const double* u, int proj, double* y, double* dx, double* du,
+                           int32_t* status, int32_t* iters);
+/* soc_projection / soc_projection_gradient alone — reference src/models/rocket/dynamics.jl:168-210.  Host pointers. */
+int od_rocket_projection_batch(od_handle* hd, int B, const double* u, double* u_proj, double* du_proj, int32_t* status);
+
+/* Number of kernels launched through this handle so far (bench.py's gpu_launches). */
+int64_t od_launch_count(const od_handle* hd);
+const char* od_last_error(void);
+const char* od_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

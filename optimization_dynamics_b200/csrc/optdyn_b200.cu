@@ -1,0 +1,408 @@
+// liboptdyn_b200.so — kernels + C ABI (include/optdyn_b200.h).  sm_100a only; there is no CPU fallback.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <new>
+#include "../../include/optdyn_b200.h"
+#include "models.cuh"
+#include "dense_ip.cuh"
+#include "rocket.cuh"
+
+namespace od {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Gradient-bundle fit: M = argmin Σ_k ‖fη_k − fz − M η_k‖²  (reference src/gradient_bundle.jl:33-47,101-102; src/ls.jl:44-60).
+// The cost is quadratic, so the reference's Newton loop converges in one step to the normal-equation solution
+// M = (Σ (fη_k − fz) η_kᵀ)(Σ η_k η_kᵀ)⁻¹; the second factor depends only on the shared perturbations and is inverted once.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void bundle_fit_kernel(int B, int N, int nq, int ncol, const double* __restrict__ feta /*B×(N+1)×nq*/, const double* __restrict__ eta /*N×ncol*/,
+                                  const double* __restrict__ Hinv /*ncol×ncol*/, const int* __restrict__ st_in /*B×(N+1)*/, double* __restrict__ dz, int* __restrict__ st_out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double* f = feta + (size_t)b * (N + 1) * nq;
+    int st = st_in[(size_t)b * (N + 1)];
+    for (int k = 0; k < N; ++k) st |= st_in[(size_t)b * (N + 1) + 1 + k];
+    for (int i = 0; i < nq; ++i) {
+        double G[16];   // ncol ≤ 16
+        for (int j = 0; j < ncol; ++j) G[j] = 0.0;
+        for (int k = 0; k < N; ++k) {
+            const double df = f[(size_t)(k + 1) * nq + i] - f[i];
+            for (int j = 0; j < ncol; ++j) G[j] += df * eta[(size_t)k * ncol + j];
+        }
+        for (int j = 0; j < ncol; ++j) {
+            double m = 0.0;
+            for (int l = 0; l < ncol; ++l) m += G[l] * Hinv[l * ncol + j];
+            dz[(size_t)b * nq * ncol + (size_t)j * nq + i] = m;
+        }
+    }
+    if (st_out) st_out[b] = st;
+}
+
+}  // namespace od
+
+using namespace od;
+
+// =====================================================================================================================
+// host side
+// =====================================================================================================================
+static thread_local char g_err[512] = "";
+static int fail(const char* what, cudaError_t e = cudaSuccess) {
+    if (e != cudaSuccess) snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(g_err, sizeof(g_err), "%s", what);
+    return 1;
+}
+#define OD_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(#call, e_); } while (0)
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct od_handle {
+    int model, device;
+    double h;
+    od_options opts;
+    double params[4];
+    cudaStream_t stream; bool own_stream;
+    DevBuf in, out, st, aux, aux2;
+    int64_t launches;
+};
+
+struct Dims { int nq, nu, nz, nth, nf; };
+static bool dims_of(int model, Dims* d) {
+    switch (model) {
+        case OD_ACROBOT_IMPACT: *d = {2, 1, 6, 6, 0}; return true;
+        case OD_ACROBOT_NOMINAL: *d = {2, 1, 2, 6, 0}; return true;
+        case OD_CARTPOLE_FRICTION: *d = {2, 1, 10, 8, 2}; return true;
+        case OD_CARTPOLE_FRICTIONLESS: *d = {2, 1, 2, 6, 0}; return true;
+        case OD_PLANAR_PUSH: *d = {5, 2, 35, 13, 0}; return true;
+        case OD_HOPPER: *d = {4, 2, 20, 13, 2}; return true;
+        case OD_ROCKET: *d = {12, 3, 12, 16, 0}; return true;
+    }
+    return false;
+}
+
+extern "C" {
+
+const char* od_last_error(void) { return g_err; }
+const char* od_version(void) { return "optdyn_b200 0.1 (sm_100a)"; }
+
+int od_default_options(int model, od_options* o) {
+    Dims d; if (!o || !dims_of(model, &d)) return fail("od_default_options: bad model");
+    o->r_tol = 1e-8; o->ls_scale = 0.5; o->max_iter = 100; o->max_ls = 25;
+    o->kappa_eval_tol = 1e-4; o->kappa_grad_tol = 1e-3;                       // examples/{acrobot,cartpole,hopper}.jl
+    if (model == OD_PLANAR_PUSH) o->kappa_grad_tol = 1e-2;                    // examples/planar_push.jl:21-22
+    if (model == OD_ROCKET) o->kappa_grad_tol = 1e-4;                         // projection κ_tol (rocket/dynamics.jl:79)
+    return 0;
+}
+
+int od_model_dims(int model, int* nq, int* nu, int* nz, int* nth) {
+    Dims d; if (!dims_of(model, &d)) return fail("od_model_dims: bad model");
+    if (nq) *nq = d.nq; if (nu) *nu = d.nu; if (nz) *nz = d.nz; if (nth) *nth = d.nth;
+    return 0;
+}
+
+od_handle* od_create(int model, double h, const od_options* opts, const double* params, int nparams, int device) {
+    Dims d;
+    if (!dims_of(model, &d)) { fail("od_create: bad model"); return nullptr; }
+    if (!(h > 0.0)) { fail("od_create: h must be positive"); return nullptr; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { fail("od_create: no CUDA device (this library has no CPU fallback)", e); return nullptr; }
+    if (device < 0 || device >= ndev) { fail("od_create: bad device ordinal"); return nullptr; }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { fail("cudaSetDevice", e); return nullptr; }
+    od_handle* hd = new (std::nothrow) od_handle();
+    if (!hd) { fail("od_create: out of memory"); return nullptr; }
+    hd->model = model; hd->device = device; hd->h = h; hd->launches = 0;
+    if (opts) hd->opts = *opts; else od_default_options(model, &hd->opts);
+    for (int k = 0; k < 4; ++k) hd->params[k] = 0.0;
+    if (model == OD_CARTPOLE_FRICTION) { hd->params[0] = 0.1; hd->params[1] = 0.1; }      // cartpole/model.jl:132
+    if (model == OD_HOPPER) { hd->params[0] = 0.5; hd->params[1] = 0.5; }                 // DESIGN.md §Hopper constants
+    if (model == OD_ROCKET) hd->params[0] = 12.5;                                         // examples/rocket.jl:16
+    for (int k = 0; k < nparams && k < 4 && params; ++k) hd->params[k] = params[k];
+    if ((e = cudaStreamCreateWithFlags(&hd->stream, cudaStreamNonBlocking)) != cudaSuccess) { fail("cudaStreamCreate", e); delete hd; return nullptr; }
+    hd->own_stream = true;
+    return hd;
+}
+
+void od_destroy(od_handle* hd) {
+    if (!hd) return;
+    cudaSetDevice(hd->device);
+    cudaStreamSynchronize(hd->stream);
+    hd->in.release(); hd->out.release(); hd->st.release(); hd->aux.release(); hd->aux2.release();
+    if (hd->own_stream) cudaStreamDestroy(hd->stream);
+    delete hd;
+}
+
+int od_set_stream(od_handle* hd, void* s) {
+    if (!hd) return fail("od_set_stream: null handle");
+    if (hd->own_stream) { cudaStreamSynchronize(hd->stream); cudaStreamDestroy(hd->stream); hd->own_stream = false; }
+    hd->stream = (cudaStream_t)s;
+    return 0;
+}
+
+int od_synchronize(od_handle* hd) {
+    if (!hd) return fail("od_synchronize: null handle");
+    OD_CUDA(cudaStreamSynchronize(hd->stream));
+    return 0;
+}
+
+int64_t od_launch_count(const od_handle* hd) { return hd ? hd->launches : 0; }
+
+}  // extern "C"
+
+template <class M>
+static cudaError_t launch_contact(const StepArgs& a, cudaStream_t s) {
+    constexpr int BLOCK = 32;
+    const int grid = (a.B + BLOCK - 1) / BLOCK;
+    constexpr size_t smem = sizeof(double) * BLOCK * ContactIP<M>::WS;
+
+    if (smem > 48 * 1024) {   // > 48 KB of dynamic shared memory needs an explicit opt-in (planar push: 112 KB); per device, so set at every launch
+        cudaError_t e = cudaFuncSetAttribute(contact_step_kernel<M, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    contact_step_kernel<M, BLOCK><<<grid, BLOCK, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+static int launch_step(od_handle* hd, StepArgs& a) {
+    if (a.B <= 0) return 0;
+    a.h = hd->h;
+    for (int k = 0; k < 4; ++k) a.fric[k] = hd->params[k];
+    a.opts.r_tol = hd->opts.r_tol; a.opts.kappa_eval_tol = hd->opts.kappa_eval_tol; a.opts.kappa_grad_tol = hd->opts.kappa_grad_tol;
+    a.opts.ls_scale = hd->opts.ls_scale; a.opts.max_iter = hd->opts.max_iter; a.opts.max_ls = hd->opts.max_ls;
+    cudaError_t e;
+    switch (hd->model) {
+        case OD_ACROBOT_IMPACT: e = launch_contact<AcrobotImpactModel>(a, hd->stream); break;
+        case OD_ACROBOT_NOMINAL: e = launch_contact<AcrobotNominalModel>(a, hd->stream); break;
+        case OD_CARTPOLE_FRICTION: e = launch_contact<CartpoleFrictionModel>(a, hd->stream); break;
+        case OD_CARTPOLE_FRICTIONLESS: e = launch_contact<CartpoleFrictionlessModel>(a, hd->stream); break;
+        case OD_PLANAR_PUSH: e = launch_contact<PlanarPushModel>(a, hd->stream); break;
+        case OD_HOPPER: e = launch_contact<HopperModel>(a, hd->stream); break;
+        default: return fail("this entry point needs a contact model handle (not OD_ROCKET)");
+    }
+    if (e != cudaSuccess) return fail("contact_step_kernel launch", e);
+    hd->launches++;
+    return 0;
+}
+
+extern "C" {
+
+int od_step_grad_batch_device(od_handle* hd, int B, const double* q1, const double* q2, const double* u,
+                              double* q3, double* dq1, double* dq2, double* du, int32_t* status, int32_t* iters, int want_eval, int want_grad) {
+    if (!hd) return fail("null handle");
+    Dims d; dims_of(hd->model, &d);
+    if (want_grad && !(dq1 && dq2 && du)) return fail("od_step_grad_batch_device: gradient outputs must all be non-null");
+    OD_CUDA(cudaSetDevice(hd->device));
+    StepArgs a; memset(&a, 0, sizeof(a));
+    a.B = B; a.q1 = q1; a.q2 = q2; a.u = u; a.in_stride_q = d.nq; a.in_stride_u = d.nu;
+    a.q3 = q3; a.dq1 = want_grad ? dq1 : nullptr; a.dq2 = dq2; a.du = du;
+    a.out_stride_q3 = d.nq; a.out_stride_dq = d.nq * d.nq; a.out_stride_du = d.nq * d.nu;
+    a.status = status; a.iters = iters; a.want_eval = want_eval; a.want_grad = want_grad;
+    return launch_step(hd, a);
+}
+
+int od_step_grad_packed_device(od_handle* hd, int B, const double* in, double* out, int32_t* status, int32_t* iters, int want_eval, int want_grad) {
+    if (!hd) return fail("null handle");
+    Dims d; dims_of(hd->model, &d);
+    OD_CUDA(cudaSetDevice(hd->device));
+    const int inw = 2 * d.nq + d.nu, outw = d.nq + d.nq * inw;
+    StepArgs a; memset(&a, 0, sizeof(a));
+    a.B = B; a.q1 = in; a.q2 = in + d.nq; a.u = in + 2 * d.nq; a.in_stride_q = inw; a.in_stride_u = inw;
+    a.q3 = out; a.dq1 = want_grad ? out + d.nq : nullptr; a.dq2 = out + d.nq + d.nq * d.nq; a.du = out + d.nq + 2 * d.nq * d.nq;
+    a.out_stride_q3 = outw; a.out_stride_dq = outw; a.out_stride_du = outw;
+    a.status = status; a.iters = iters; a.want_eval = want_eval; a.want_grad = want_grad;
+    return launch_step(hd, a);
+}
+
+int od_step_grad_packed(od_handle* hd, int B, const double* in, double* out, int32_t* status) {
+    if (!hd) return fail("null handle");
+    Dims d; dims_of(hd->model, &d);
+    if (hd->model == OD_ROCKET) return fail("od_step_grad_packed: use od_rocket_batch for OD_ROCKET");
+    if (B <= 0) return 0;
+    OD_CUDA(cudaSetDevice(hd->device));
+    const size_t inw = 2 * d.nq + d.nu, outw = d.nq + d.nq * inw;
+    OD_CUDA(hd->in.reserve(sizeof(double) * inw * B));
+    OD_CUDA(hd->out.reserve(sizeof(double) * outw * B));
+    OD_CUDA(hd->st.reserve(sizeof(int32_t) * B));
+    OD_CUDA(cudaMemcpyAsync(hd->in.p, in, sizeof(double) * inw * B, cudaMemcpyHostToDevice, hd->stream));
+    if (od_step_grad_packed_device(hd, B, (const double*)hd->in.p, (double*)hd->out.p, (int32_t*)hd->st.p, nullptr, 1, 1)) return 1;
+    OD_CUDA(cudaMemcpyAsync(out, hd->out.p, sizeof(double) * outw * B, cudaMemcpyDeviceToHost, hd->stream));
+    if (status) OD_CUDA(cudaMemcpyAsync(status, hd->st.p, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, hd->stream));
+    OD_CUDA(cudaStreamSynchronize(hd->stream));
+    return 0;
+}
+
+int od_step_grad_batch(od_handle* hd, int B, const double* q1, const double* q2, const double* u,
+                       double* q3, double* dq1, double* dq2, double* du, int32_t* status) {
+    if (!hd) return fail("null handle");
+    Dims d; dims_of(hd->model, &d);
+    if (hd->model == OD_ROCKET) return fail("od_step_grad_batch: use od_rocket_batch for OD_ROCKET");
+    if (B <= 0) return 0;
+    const bool want_grad = dq1 || dq2 || du;
+    if (want_grad && !(dq1 && dq2 && du)) return fail("od_step_grad_batch: gradient outputs must be all null or all non-null");
+    if (!want_grad && !q3) return fail("od_step_grad_batch: nothing to compute");
+    OD_CUDA(cudaSetDevice(hd->device));
+    const size_t nq = d.nq, nu = d.nu, inw = 2 * nq + nu, outw = nq + nq * inw;
+    OD_CUDA(hd->in.reserve(sizeof(double) * inw * B));
+    OD_CUDA(hd->out.reserve(sizeof(double) * outw * B));
+    OD_CUDA(hd->st.reserve(sizeof(int32_t) * B));
+    double* din = (double*)hd->in.p; double* dout = (double*)hd->out.p;
+    double *d_q1 = din, *d_q2 = din + nq * B, *d_u = din + 2 * nq * B;
+    double *d_q3 = dout, *d_dq1 = dout + nq * B, *d_dq2 = d_dq1 + nq * nq * B, *d_du = d_dq2 + nq * nq * B;
+    OD_CUDA(cudaMemcpyAsync(d_q1, q1, sizeof(double) * nq * B, cudaMemcpyHostToDevice, hd->stream));
+    OD_CUDA(cudaMemcpyAsync(d_q2, q2, sizeof(double) * nq * B, cudaMemcpyHostToDevice, hd->stream));
+    OD_CUDA(cudaMemcpyAsync(d_u, u, sizeof(double) * nu * B, cudaMemcpyHostToDevice, hd->stream));
+    if (od_step_grad_batch_device(hd, B, d_q1, d_q2, d_u, q3 ? d_q3 : nullptr, d_dq1, d_dq2, d_du, (int32_t*)hd->st.p, nullptr, q3 != nullptr, want_grad)) return 1;
+    if (q3) OD_CUDA(cudaMemcpyAsync(q3, d_q3, sizeof(double) * nq * B, cudaMemcpyDeviceToHost, hd->stream));
+    if (want_grad) {
+        OD_CUDA(cudaMemcpyAsync(dq1, d_dq1, sizeof(double) * nq * nq * B, cudaMemcpyDeviceToHost, hd->stream));
+        OD_CUDA(cudaMemcpyAsync(dq2, d_dq2, sizeof(double) * nq * nq * B, cudaMemcpyDeviceToHost, hd->stream));
+        OD_CUDA(cudaMemcpyAsync(du, d_du, sizeof(double) * nq * nu * B, cudaMemcpyDeviceToHost, hd->stream));
+    }
+    if (status) OD_CUDA(cudaMemcpyAsync(status, hd->st.p, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, hd->stream));
+    OD_CUDA(cudaStreamSynchronize(hd->stream));
+    return 0;
+}
+
+int od_step_batch(od_handle* hd, int B, const double* q1, const double* q2, const double* u, double* q3, int32_t* status) {
+    if (!q3) return fail("od_step_batch: q3 is null");
+    return od_step_grad_batch(hd, B, q1, q2, u, q3, nullptr, nullptr, nullptr, status);
+}
+
+int od_bundle_batch(od_handle* hd, int B, int N, const double* eta, const double* q1, const double* q2, const double* u, double* dz, int32_t* status) {
+    if (!hd) return fail("null handle");
+    Dims d; dims_of(hd->model, &d);
+    if (hd->model == OD_ROCKET) return fail("od_bundle_batch: contact models only");
+    if (B <= 0) return 0;
+    if (N <= 0 || !eta || !dz) return fail("od_bundle_batch: need N > 0, eta and dz");
+    const int nq = d.nq, nu = d.nu, ncol = 2 * nq + nu;
+    if (ncol > 16) return fail("od_bundle_batch: 2nq+nu > 16 unsupported");
+    // H = Σ η ηᵀ, inverted on the host by Gauss–Jordan with partial pivoting (ncol ≤ 12)
+    double H[16 * 16], Hi[16 * 16];
+    for (int i = 0; i < ncol * ncol; ++i) { H[i] = 0.0; Hi[i] = 0.0; }
+    for (int k = 0; k < N; ++k) for (int i = 0; i < ncol; ++i) for (int j = 0; j < ncol; ++j) H[i * ncol + j] += eta[(size_t)k * ncol + i] * eta[(size_t)k * ncol + j];
+    for (int i = 0; i < ncol; ++i) Hi[i * ncol + i] = 1.0;
+    bool singular = false;
+    for (int k = 0; k < ncol && !singular; ++k) {
+        int p = k; double best = fabs(H[k * ncol + k]);
+        for (int i = k + 1; i < ncol; ++i) if (fabs(H[i * ncol + k]) > best) { best = fabs(H[i * ncol + k]); p = i; }
+        if (!(best > 0.0)) { singular = true; break; }
+        if (p != k) for (int j = 0; j < ncol; ++j) { double t = H[k * ncol + j]; H[k * ncol + j] = H[p * ncol + j]; H[p * ncol + j] = t; t = Hi[k * ncol + j]; Hi[k * ncol + j] = Hi[p * ncol + j]; Hi[p * ncol + j] = t; }
+        const double inv = 1.0 / H[k * ncol + k];
+        for (int j = 0; j < ncol; ++j) { H[k * ncol + j] *= inv; Hi[k * ncol + j] *= inv; }
+        for (int i = 0; i < ncol; ++i) if (i != k) {
+            const double l = H[i * ncol + k];
+            if (l != 0.0) for (int j = 0; j < ncol; ++j) { H[i * ncol + j] -= l * H[k * ncol + j]; Hi[i * ncol + j] -= l * Hi[k * ncol + j]; }
+        }
+    }
+    if (singular) {   // the reference's LU would divide by zero here (a coordinate that no perturbation touches)
+        if (status) for (int b = 0; b < B; ++b) status[b] = 8;
+        return fail("od_bundle_batch: Σηηᵀ is singular (some coordinate is never perturbed)");
+    }
+    OD_CUDA(cudaSetDevice(hd->device));
+    const size_t P = (size_t)B * (N + 1);
+    const size_t inw = ncol;
+    OD_CUDA(hd->in.reserve(sizeof(double) * inw * B));
+    OD_CUDA(hd->aux.reserve(sizeof(double) * ((size_t)N * ncol + ncol * ncol)));
+    OD_CUDA(hd->aux2.reserve(sizeof(double) * P * nq + sizeof(int32_t) * P));
+    OD_CUDA(hd->out.reserve(sizeof(double) * (size_t)B * nq * ncol));
+    OD_CUDA(hd->st.reserve(sizeof(int32_t) * B));
+    double* din = (double*)hd->in.p;
+    double *d_q1 = din, *d_q2 = din + (size_t)nq * B, *d_u = din + (size_t)2 * nq * B;
+    double* d_eta = (double*)hd->aux.p; double* d_Hi = d_eta + (size_t)N * ncol;
+    double* d_f = (double*)hd->aux2.p; int32_t* d_st = (int32_t*)(d_f + P * nq);
+    OD_CUDA(cudaMemcpyAsync(d_q1, q1, sizeof(double) * nq * B, cudaMemcpyHostToDevice, hd->stream));
+    OD_CUDA(cudaMemcpyAsync(d_q2, q2, sizeof(double) * nq * B, cudaMemcpyHostToDevice, hd->stream));
+    OD_CUDA(cudaMemcpyAsync(d_u, u, sizeof(double) * nu * B, cudaMemcpyHostToDevice, hd->stream));
+    OD_CUDA(cudaMemcpyAsync(d_eta, eta, sizeof(double) * N * ncol, cudaMemcpyHostToDevice, hd->stream));
+    OD_CUDA(cudaMemcpyAsync(d_Hi, Hi, sizeof(double) * ncol * ncol, cudaMemcpyHostToDevice, hd->stream));
+    StepArgs a; memset(&a, 0, sizeof(a));
+    a.B = (int)P; a.q1 = d_q1; a.q2 = d_q2; a.u = d_u; a.in_stride_q = nq; a.in_stride_u = nu;
+    a.q3 = d_f; a.out_stride_q3 = nq; a.status = d_st; a.want_eval = 1; a.want_grad = 0; a.eta = d_eta; a.n_eta = N;
+    if (launch_step(hd, a)) return 1;
+    bundle_fit_kernel<<<(B + 63) / 64, 64, 0, hd->stream>>>(B, N, nq, ncol, d_f, d_eta, d_Hi, d_st, (double*)hd->out.p, (int32_t*)hd->st.p);
+    OD_CUDA(cudaGetLastError());
+    hd->launches++;
+    OD_CUDA(cudaMemcpyAsync(dz, hd->out.p, sizeof(double) * (size_t)B * nq * ncol, cudaMemcpyDeviceToHost, hd->stream));
+    if (status) OD_CUDA(cudaMemcpyAsync(status, hd->st.p, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, hd->stream));
+    OD_CUDA(cudaStreamSynchronize(hd->stream));
+    return 0;
+}
+
+static int launch_rocket(od_handle* hd, RocketArgs& a) {
+    if (hd->model != OD_ROCKET) return fail("rocket entry point needs an OD_ROCKET handle");
+    if (a.B <= 0) return 0;
+    a.h = hd->h; a.u_max = hd->params[0];
+    a.opts.r_tol = hd->opts.r_tol; a.opts.kappa_eval_tol = hd->opts.kappa_eval_tol; a.opts.kappa_grad_tol = hd->opts.kappa_grad_tol;
+    a.opts.ls_scale = hd->opts.ls_scale; a.opts.max_iter = hd->opts.max_iter; a.opts.max_ls = hd->opts.max_ls;
+    constexpr int BLOCK = 32;
+    rocket_kernel<BLOCK><<<(a.B + BLOCK - 1) / BLOCK, BLOCK, 0, hd->stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("rocket_kernel launch", e);
+    hd->launches++;
+    return 0;
+}
+
+int od_rocket_batch_device(od_handle* hd, int B, const double* x, const double* u, int proj, double* y, double* dx, double* du, int32_t* status, int32_t* iters) {
+    if (!hd) return fail("null handle");
+    OD_CUDA(cudaSetDevice(hd->device));
+    RocketArgs a; memset(&a, 0, sizeof(a));
+    a.B = B; a.x = x; a.u = u; a.y = y; a.dx = dx; a.du = du; a.status = status; a.iters = iters; a.proj = proj; a.want_grad = (dx || du) ? 1 : 0;
+    return launch_rocket(hd, a);
+}
+
+int od_rocket_batch(od_handle* hd, int B, const double* x, const double* u, int proj, double* y, double* dx, double* du, int32_t* status) {
+    if (!hd) return fail("null handle");
+    if (hd->model != OD_ROCKET) return fail("od_rocket_batch needs an OD_ROCKET handle");
+    if (B <= 0) return 0;
+    OD_CUDA(cudaSetDevice(hd->device));
+    OD_CUDA(hd->in.reserve(sizeof(double) * 15 * (size_t)B));
+    OD_CUDA(hd->out.reserve(sizeof(double) * (12 + 144 + 36) * (size_t)B));
+    OD_CUDA(hd->st.reserve(sizeof(int32_t) * B));
+    double* d_x = (double*)hd->in.p; double* d_u = d_x + (size_t)12 * B;
+    double* d_y = (double*)hd->out.p; double* d_dx = d_y + (size_t)12 * B; double* d_du = d_dx + (size_t)144 * B;
+    OD_CUDA(cudaMemcpyAsync(d_x, x, sizeof(double) * 12 * B, cudaMemcpyHostToDevice, hd->stream));
+    OD_CUDA(cudaMemcpyAsync(d_u, u, sizeof(double) * 3 * B, cudaMemcpyHostToDevice, hd->stream));
+    const bool grad = dx || du;
+    if (od_rocket_batch_device(hd, B, d_x, d_u, proj, d_y, grad ? d_dx : nullptr, grad ? d_du : nullptr, (int32_t*)hd->st.p, nullptr)) return 1;
+    if (y) OD_CUDA(cudaMemcpyAsync(y, d_y, sizeof(double) * 12 * B, cudaMemcpyDeviceToHost, hd->stream));
+    if (dx) OD_CUDA(cudaMemcpyAsync(dx, d_dx, sizeof(double) * 144 * B, cudaMemcpyDeviceToHost, hd->stream));
+    if (du) OD_CUDA(cudaMemcpyAsync(du, d_du, sizeof(double) * 36 * B, cudaMemcpyDeviceToHost, hd->stream));
+    if (status) OD_CUDA(cudaMemcpyAsync(status, hd->st.p, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, hd->stream));
+    OD_CUDA(cudaStreamSynchronize(hd->stream));
+    return 0;
+}
+
+int od_rocket_projection_batch(od_handle* hd, int B, const double* u, double* up, double* dup, int32_t* status) {
+    if (!hd) return fail("null handle");
+    if (hd->model != OD_ROCKET) return fail("od_rocket_projection_batch needs an OD_ROCKET handle");
+    if (B <= 0) return 0;
+    OD_CUDA(cudaSetDevice(hd->device));
+    OD_CUDA(hd->in.reserve(sizeof(double) * 3 * (size_t)B));
+    OD_CUDA(hd->out.reserve(sizeof(double) * 12 * (size_t)B));
+    OD_CUDA(hd->st.reserve(sizeof(int32_t) * B));
+    double* d_u = (double*)hd->in.p; double* d_up = (double*)hd->out.p; double* d_dup = d_up + (size_t)3 * B;
+    OD_CUDA(cudaMemcpyAsync(d_u, u, sizeof(double) * 3 * B, cudaMemcpyHostToDevice, hd->stream));
+    RocketArgs a; memset(&a, 0, sizeof(a));
+    a.B = B; a.u = d_u; a.uproj = d_up; a.duproj = d_dup; a.status = (int32_t*)hd->st.p; a.proj = 1; a.proj_only = 1; a.want_grad = dup ? 1 : 0;
+    if (launch_rocket(hd, a)) return 1;
+    if (up) OD_CUDA(cudaMemcpyAsync(up, d_up, sizeof(double) * 3 * B, cudaMemcpyDeviceToHost, hd->stream));
+    if (dup) OD_CUDA(cudaMemcpyAsync(dup, d_dup, sizeof(double) * 9 * B, cudaMemcpyDeviceToHost, hd->stream));
+    if (status) OD_CUDA(cudaMemcpyAsync(status, hd->st.p, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, hd->stream));
+    OD_CUDA(cudaStreamSynchronize(hd->stream));
+    return 0;
+}
+
+}  // extern "C"

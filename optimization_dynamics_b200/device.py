@@ -1,0 +1,96 @@
+"""Device-resident batched stepping (torch tensors are only the memory/stream plumbing) and single-node multi-GPU sharding.
+
+The derivative sweep of iLQR evaluates fx/fu at every timestep independently; the Riccati backward pass then
+needs all of them.  Each rank solves a contiguous slice of the batch and ONE NCCL all-gather of the packed output rows
+(hopper: 44 doubles = 352 B per problem) gives every rank the full set — there is no other data-path communication.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .dynamics import ImplicitDynamics
+
+
+def shard_range(B, rank, world):
+    """Contiguous slice [lo, hi) of a batch of B problems owned by `rank`; sizes differ by at most one."""
+    base, rem = divmod(B, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_sizes(B, world):
+    return [shard_range(B, r, world)[1] - shard_range(B, r, world)[0] for r in range(world)]
+
+
+def all_gather_rows(local, B_total, gathered=None):
+    """All-gather contiguous row shards (shard_range) of a [B_total, W] matrix; one collective.  Ragged shards (B_total not a
+    multiple of the world size) are padded by one row to the largest shard and compacted after the collective."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    sizes = shard_sizes(B_total, world)
+    W = local.shape[1]
+    if gathered is None:
+        gathered = torch.empty((B_total, W), dtype=local.dtype, device=local.device)
+    if len(set(sizes)) == 1:
+        dist.all_gather_into_tensor(gathered, local)
+        return gathered
+    m = max(sizes)
+    padded = torch.zeros((m, W), dtype=local.dtype, device=local.device)
+    padded[:local.shape[0]] = local
+    buf = torch.empty((world * m, W), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(buf, padded)
+    lo = 0
+    for r, n in enumerate(sizes):
+        gathered[lo:lo + n] = buf[r * m:r * m + n]
+        lo += n
+    return gathered
+
+
+class DeviceStepper:
+    """Runs the packed step+gradient kernel on torch CUDA tensors, on torch's current stream."""
+
+    def __init__(self, im_dyn: ImplicitDynamics):
+        import torch
+        self.torch = torch
+        self.dyn = im_dyn
+        self.nq, self.nu = im_dyn.nq, im_dyn.nu
+        self.in_width = 2 * self.nq + self.nu
+        self.out_width = self.nq + self.nq * self.in_width
+
+    def _bind_stream(self):
+        s = self.torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().od_set_stream(self.dyn._handle(), C.c_void_p(s)))
+
+    def step_grad_packed(self, xin, out=None, status=None, iters=None, want_eval=True, want_grad=True):
+        """xin: [B, 2nq+nu] float64 CUDA tensor → out [B, nq + nq(2nq+nu)], status [B] int32.  Asynchronous."""
+        t = self.torch
+        assert xin.is_cuda and xin.dtype == t.float64 and xin.is_contiguous() and xin.shape[1] == self.in_width
+        B = xin.shape[0]
+        if out is None:
+            out = t.empty((B, self.out_width), dtype=t.float64, device=xin.device)
+        if status is None:
+            status = t.empty((B,), dtype=t.int32, device=xin.device)
+        self._bind_stream()
+        _lib.check(_lib.lib().od_step_grad_packed_device(self.dyn._handle(), B, C.c_void_p(xin.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                         C.c_void_p(status.data_ptr()), C.c_void_p(iters.data_ptr()) if iters is not None else None,
+                                                         int(want_eval), int(want_grad)))
+        return out, status
+
+    def step_grad_sharded(self, xin_local, B_total, gathered=None):
+        """Each rank passes its slice (shard_range) of the packed inputs; returns the all-gathered [B_total, out_width] outputs."""
+        out_local, status = self.step_grad_packed(xin_local)
+        return all_gather_rows(out_local, B_total, gathered), status
+
+
+def unpack_outputs(out, nq, nu):
+    """Split packed rows into q3 [B,nq] and Jacobians [B,nq,nq], [B,nq,nq], [B,nq,nu] (row = q3 component).  numpy or torch."""
+    B = out.shape[0]
+    o = nq
+    q3 = out[:, :nq]
+    d1 = out[:, o:o + nq * nq].reshape(B, nq, nq)
+    d2 = out[:, o + nq * nq:o + 2 * nq * nq].reshape(B, nq, nq)
+    du = out[:, o + 2 * nq * nq:].reshape(B, nu, nq)
+    tr = (lambda a: a.transpose(0, 2, 1)) if isinstance(out, np.ndarray) else (lambda a: a.transpose(1, 2))
+    return q3, tr(d1), tr(d2), tr(du)

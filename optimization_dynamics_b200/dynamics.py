@@ -1,0 +1,197 @@
+"""Host-side mirror of the reference's implicit-dynamics API over the C ABI.
+
+Same names, argument order and semantics as the reference's Julia code:
+    ImplicitDynamics(model, h, r, rz, rθ; T, r_tol, κ_eval_tol, κ_grad_tol, no_impact, no_friction, n, m, d, nc, nb, info)
+                                                             reference src/dynamics.jl:51-79
+    f(d, model, x, u, w) / fx(dx, …) / fu(du, …)             reference src/dynamics.jl:81-128
+    state_to_configuration(x)                                reference src/dynamics.jl:131-145
+plus the batched calls the CUDA path is built for (`step_grad_batch`): all timesteps × samples × rollouts in one launch.
+The three generated-function arguments of the reference constructor (r, rz, rθ) are accepted and ignored: the residual code
+is compiled into the library (csrc/gen/).  There is no CPU fallback — construction raises without a CUDA device.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+MODEL_IDS = {"acrobot_impact": 0, "acrobot_nominal": 1, "cartpole_friction": 2, "cartpole_frictionless": 3, "planar_push": 4,
+             "hopper": 5, "rocket": 6}
+
+
+class Model:
+    """Model singleton (reference: `acrobot_impact`, `cartpole_friction`, `planarpush`, `RoboDojo.hopper`, `rocket`, …)."""
+
+    def __init__(self, name, nq, nu, nw, nc, friction=None, **consts):
+        self.name, self.nq, self.nu, self.nw, self.nc = name, nq, nu, nw, nc
+        self.friction = None if friction is None else np.array(friction, dtype=np.float64)   # mutable, like model.friction .= μ
+        for k, v in consts.items():
+            setattr(self, k, v)
+
+    def __repr__(self):
+        return "Model(%s, nq=%d, nu=%d)" % (self.name, self.nq, self.nu)
+
+
+# reference src/models/acrobot/model.jl:159-163, cartpole/model.jl:131-132, planar_push/model.jl:196-200, rocket/model.jl:43-48
+acrobot_impact = Model("acrobot_impact", 2, 1, 0, 2)
+acrobot_nominal = Model("acrobot_nominal", 2, 1, 0, 0)
+cartpole_friction = Model("cartpole_friction", 2, 1, 0, 2, friction=[0.1, 0.1], mc=1.0, mp=0.2, l=0.5, g=9.81)
+cartpole_frictionless = Model("cartpole_frictionless", 2, 1, 0, 2, mc=1.0, mp=0.2, l=0.5, g=9.81)
+planarpush = Model("planar_push", 5, 2, 0, 5)
+hopper = Model("hopper", 4, 2, 0, 4, friction=[0.5, 0.5], mass_body=3.0, mass_foot=1.0, inertia_body=0.75, gravity=9.81,
+               body_radius=0.1, foot_radius=0.05, leg_len_max=1.0, leg_len_min=0.25)
+rocket = Model("rocket", 12, 3, 0, 0, mass=1.0, length=1.0)
+
+
+def _dp(a):
+    return a.ctypes.data_as(_lib.c_double_p)
+
+
+def _ip(a):
+    return a.ctypes.data_as(_lib.c_int32_p)
+
+
+def _f64(a, shape):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a.reshape(shape)
+
+
+class ImplicitDynamics:
+    def __init__(self, model, h, r_func=None, rz_func=None, rθ_func=None, T=1, r_tol=1.0e-8, κ_eval_tol=1.0e-6, κ_grad_tol=1.0e-6,
+                 no_impact=False, no_friction=False, n=None, m=None, d=None, nc=None, nb=None, info=None, device=0,
+                 kappa_eval_tol=None, kappa_grad_tol=None):
+        L = _lib.lib()
+        self.model = model
+        self.h = float(h)
+        self.n = 2 * model.nq if n is None else n
+        self.m = model.nu if m is None else m
+        self.d = model.nw if d is None else d
+        self.info = info
+        self.nq, self.nu = model.nq, model.nu
+        self.idx_q1 = np.arange(model.nq)
+        self.idx_q2 = model.nq + np.arange(model.nq)
+        self.idx_u1 = np.arange(model.nu)
+        opts = _lib.od_options()
+        _lib.check(L.od_default_options(MODEL_IDS[model.name], C.byref(opts)))
+        opts.r_tol = r_tol
+        opts.kappa_eval_tol = κ_eval_tol if kappa_eval_tol is None else kappa_eval_tol
+        opts.kappa_grad_tol = κ_grad_tol if kappa_grad_tol is None else kappa_grad_tol
+        self.opts = opts
+        self.device = device
+        self._friction_seen = None
+        self._hd = None
+        self._make_handle()
+        self._memo_key = None      # (x, u) of the last gradient solve: fx and fu share one launch (reference solves twice)
+        self._memo = None
+
+    # the reference mutates model.friction after construction (examples/cartpole.jl:21); re-create the handle if it changed
+    def _make_handle(self):
+        L = _lib.lib()
+        fr = self.model.friction
+        params = None if fr is None else _dp(np.ascontiguousarray(fr, dtype=np.float64))
+        hd = L.od_create(MODEL_IDS[self.model.name], self.h, C.byref(self.opts), params, 0 if fr is None else len(fr), self.device)
+        if not hd:
+            raise RuntimeError("optdyn_b200: " + L.od_last_error().decode())
+        if self._hd:
+            L.od_destroy(self._hd)
+        self._hd = hd
+        self._friction_seen = None if fr is None else fr.copy()
+
+    def _handle(self):
+        fr = self.model.friction
+        if fr is not None and not np.array_equal(fr, self._friction_seen):
+            self._make_handle()
+            self._memo_key = None
+        return self._hd
+
+    def __del__(self):
+        try:
+            if self._hd:
+                _lib.lib().od_destroy(self._hd)
+                self._hd = None
+        except Exception:
+            pass
+
+    # ---- batched API -------------------------------------------------------------------------------------------------
+    def step_batch(self, q1, q2, u):
+        """q3 for B problems (eval simulator).  Returns (q3[B,nq], status[B])."""
+        q1 = _f64(q1, (-1, self.nq)); B = q1.shape[0]
+        q2 = _f64(q2, (B, self.nq)); u = _f64(u, (B, self.nu))
+        q3 = np.empty((B, self.nq)); st = np.empty(B, dtype=np.int32)
+        _lib.check(_lib.lib().od_step_batch(self._handle(), B, _dp(q1), _dp(q2), _dp(u), _dp(q3), _ip(st)))
+        return q3, st
+
+    def step_grad_batch(self, q1, q2, u, want_q3=True):
+        """q3 and ∂q3/∂q1, ∂q3/∂q2, ∂q3/∂u1 for B problems.  Jacobians are returned as [B, nq, ncol] (row = q3 component)."""
+        q1 = _f64(q1, (-1, self.nq)); B = q1.shape[0]
+        q2 = _f64(q2, (B, self.nq)); u = _f64(u, (B, self.nu))
+        q3 = np.empty((B, self.nq)) if want_q3 else None
+        d1 = np.empty((B, self.nq, self.nq)); d2 = np.empty((B, self.nq, self.nq)); du = np.empty((B, self.nu, self.nq))
+        st = np.empty(B, dtype=np.int32)
+        _lib.check(_lib.lib().od_step_grad_batch(self._handle(), B, _dp(q1), _dp(q2), _dp(u), None if q3 is None else _dp(q3),
+                                                 _dp(d1), _dp(d2), _dp(du), _ip(st)))
+        # the ABI blocks are column-major; as C arrays they are the transposes
+        return q3, d1.transpose(0, 2, 1), d2.transpose(0, 2, 1), du.transpose(0, 2, 1), st
+
+    def step_grad_packed(self, xin, out=None, status=None):
+        """Packed rows in [q1|q2|u] → out [q3 | ∂q3/∂q1 | ∂q3/∂q2 | ∂q3/∂u1] (blocks column-major).  Fewest transfers."""
+        inw = 2 * self.nq + self.nu
+        outw = self.nq + self.nq * inw
+        xin = _f64(xin, (-1, inw)); B = xin.shape[0]
+        out = np.empty((B, outw)) if out is None else out
+        status = np.empty(B, dtype=np.int32) if status is None else status
+        _lib.check(_lib.lib().od_step_grad_packed(self._handle(), B, _dp(xin), _dp(out), _ip(status)))
+        return out, status
+
+    def launch_count(self):
+        return int(_lib.lib().od_launch_count(self._hd))
+
+    # ---- single-problem gradient with memoisation --------------------------------------------------------------------------
+    def _grad(self, x, u):
+        x = np.asarray(x, dtype=np.float64); u = np.asarray(u, dtype=np.float64)
+        key = (x.tobytes(), u.tobytes())
+        if key != self._memo_key:
+            q1 = x[self.idx_q1]; q2 = x[self.idx_q2]
+            _, d1, d2, du, st = self.step_grad_batch(q1[None], q2[None], u[self.idx_u1][None], want_q3=False)
+            self._memo_key, self._memo = key, (d1[0], d2[0], du[0], int(st[0]))
+        return self._memo
+
+
+def f(d, model, x, u, w):
+    """d = [q2; q3] — reference src/dynamics.jl:81-94."""
+    x = np.asarray(x, dtype=np.float64)
+    q1 = x[model.idx_q1]; q2 = x[model.idx_q2]
+    q3, _ = model.step_batch(q1[None], q2[None], np.asarray(u, dtype=np.float64)[model.idx_u1][None])
+    d[model.idx_q1] = q2
+    d[model.idx_q2] = q3[0]
+    return d
+
+
+def fx(dx, model, x, u, w):
+    """dx = [0 I; ∂q3∂q1 ∂q3∂q2]; only these blocks are written (reference src/dynamics.jl:96-114)."""
+    d1, d2, _, _ = model._grad(x, u)
+    nq = model.nq
+    for i in range(nq):
+        dx[model.idx_q1[i], model.idx_q2[i]] = 1.0
+    dx[np.ix_(model.idx_q2, model.idx_q1)] = d1
+    dx[np.ix_(model.idx_q2, model.idx_q2)] = d2
+    return dx
+
+
+def fu(du, model, x, u, w):
+    """du[q2 rows, :] = ∂q3∂u1 (reference src/dynamics.jl:116-128)."""
+    _, _, dU, _ = model._grad(x, u)
+    du[model.idx_q2, :] = dU
+    return du
+
+
+def state_to_configuration(x):
+    """[x[1][1:nq], x[1][nq+1:2nq], x[2][nq+1:2nq], …] — reference src/dynamics.jl:131-145."""
+    nq = len(x[0]) // 2
+    q = []
+    for t, xt in enumerate(x):
+        xt = np.asarray(xt)
+        if t == 0:
+            q.append(xt[:nq].copy())
+        q.append(xt[nq:2 * nq].copy())
+    return q

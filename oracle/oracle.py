@@ -1,0 +1,122 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED (oracle/README.md).
+
+ctypes front-end of oracle/liboracle.so (the C++ fp64 restatement of the reference's CPU path).  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module; the product package
+(optimization_dynamics_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+MODELS = {"acrobot_impact": 0, "acrobot_nominal": 1, "cartpole_friction": 2, "cartpole_frictionless": 3,
+          "planar_push": 4, "hopper": 5, "rocket": 6, "rocket_proj": 7}
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_api.cpp", "ip.hpp", "models.hpp", "dual.hpp")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+    return _LIB
+
+
+def _p(a, t=C.c_double):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+def dims(model):
+    nq, nu, nz, nth = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    assert lib().od_oracle_dims(MODELS[model], C.byref(nq), C.byref(nu), C.byref(nz), C.byref(nth)) == 0
+    return nq.value, nu.value, nz.value, nth.value
+
+
+def residual(model, z, th, kappa=0.0):
+    mid = MODELS[model]
+    nz, nth = len(z), len(th)
+    z = np.ascontiguousarray(z, dtype=np.float64); th = np.ascontiguousarray(th, dtype=np.float64)
+    r = np.zeros(nz); rz = np.zeros((nz, nz)); rth = np.zeros((nz, nth))
+    assert lib().od_oracle_residual(mid, _p(z), _p(th), C.c_double(kappa), _p(r), _p(rz), _p(rth)) == 0
+    return r, rz, rth
+
+
+def step_batch(model, q1, q2, u, h, kappa_tol, diff, fric=None, r_tol=1e-8, nthreads=0, full=False):
+    """Returns dict(q3, dq1, dq2, du (column-major per problem, as (B, ncol, nq) arrays), iters, status, ls, r_vio, k_vio, margin)."""
+    mid = MODELS[model]
+    nq, nu, nz, nth = dims(model)
+    q1 = np.ascontiguousarray(q1, dtype=np.float64).reshape(-1, nq); B = q1.shape[0]
+    q2 = np.ascontiguousarray(q2, dtype=np.float64).reshape(B, nq)
+    u = np.ascontiguousarray(u, dtype=np.float64).reshape(B, nu)
+    fr = None if fric is None else np.ascontiguousarray(fric, dtype=np.float64)
+    q3 = np.zeros((B, nq)); info = np.zeros((B, 4), dtype=np.int32); vio = np.zeros((B, 4))
+    dq1 = dq2 = du = dzf = None
+    if diff:
+        dq1 = np.zeros((B, nq, nq)); dq2 = np.zeros((B, nq, nq)); du = np.zeros((B, nu, nq))
+        if full:
+            dzf = np.zeros((B, nz, nth))
+    zout = np.zeros((B, nz))
+    rc = lib().od_oracle_step_batch(mid, B, _p(q1), _p(q2), _p(u), _p(fr), C.c_double(h), C.c_double(r_tol), C.c_double(kappa_tol),
+                                    int(bool(diff)), _p(q3), _p(dq1), _p(dq2), _p(du), _p(dzf), _p(zout), _p(info, C.c_int), _p(vio), int(nthreads))
+    assert rc == 0
+    return dict(q3=q3, dq1=dq1, dq2=dq2, du=du, dz_full=dzf, z=zout, iters=info[:, 0].copy(), status=info[:, 1].copy(), ls=info[:, 2].copy(),
+                r_vio=vio[:, 0].copy(), k_vio=vio[:, 1].copy(), margin=vio[:, 2].copy(), ift_spread=vio[:, 3].copy())
+
+
+def rocket_batch(x, u, h, u_max, proj, diff, nthreads=0):
+    x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 12); B = x.shape[0]
+    u = np.ascontiguousarray(u, dtype=np.float64).reshape(B, 3)
+    y = np.zeros((B, 12)); dx = np.zeros((B, 12, 12)) if diff else None; du = np.zeros((B, 3, 12)) if diff else None
+    up = np.zeros((B, 3)); info = np.zeros((B, 4), dtype=np.int32); vio = np.zeros((B, 3))
+    rc = lib().od_oracle_rocket_batch(B, _p(x), _p(u), C.c_double(h), C.c_double(u_max), int(bool(proj)), int(bool(diff)),
+                                      _p(y), _p(dx), _p(du), _p(up), _p(info, C.c_int), _p(vio), int(nthreads))
+    assert rc == 0
+    return dict(y=y, dx=dx, du=du, uproj=up, iters=info[:, 0].copy(), status=info[:, 1].copy(), proj_iters=info[:, 3].copy(), margin=vio[:, 2].copy(),
+                r_vio=vio[:, 0].copy())
+
+
+def rocket_projection_batch(u, u_max, diff=True):
+    u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1, 3); B = u.shape[0]
+    up = np.zeros((B, 3)); dp = np.zeros((B, 3, 3)); info = np.zeros((B, 4), dtype=np.int32); vio = np.zeros((B, 3))
+    rc = lib().od_oracle_rocket_projection_batch(B, _p(u), C.c_double(u_max), int(bool(diff)), _p(up), _p(dp), _p(info, C.c_int), _p(vio))
+    assert rc == 0
+    return dict(up=up, dproj=dp, iters=info[:, 0].copy(), status=info[:, 1].copy(), margin=vio[:, 2].copy(), k_vio=vio[:, 1].copy())
+
+
+def bundle_batch(model, eta, q1, q2, u, h, kappa_tol, fric=None, r_tol=1e-8, nthreads=0):
+    mid = MODELS[model]
+    nq, nu, nz, nth = dims(model)
+    ncol = 2 * nq + nu
+    eta = np.ascontiguousarray(eta, dtype=np.float64).reshape(-1, ncol); N = eta.shape[0]
+    q1 = np.ascontiguousarray(q1, dtype=np.float64).reshape(-1, nq); B = q1.shape[0]
+    q2 = np.ascontiguousarray(q2, dtype=np.float64).reshape(B, nq)
+    u = np.ascontiguousarray(u, dtype=np.float64).reshape(B, nu)
+    fr = None if fric is None else np.ascontiguousarray(fric, dtype=np.float64)
+    dz = np.zeros((B, ncol, nq)); st = np.zeros(B, dtype=np.int32)
+    rc = lib().od_oracle_bundle_batch(mid, B, N, _p(eta), _p(q1), _p(q2), _p(u), _p(fr), C.c_double(h), C.c_double(r_tol), C.c_double(kappa_tol),
+                                      _p(dz), _p(st, C.c_int), int(nthreads))
+    assert rc == 0
+    return dict(dz=dz, status=st)
+
+
+def least_squares(fz, feta, eta):
+    fz = np.ascontiguousarray(fz, dtype=np.float64); ny = fz.shape[0]
+    feta = np.ascontiguousarray(feta, dtype=np.float64).reshape(-1, ny); N = feta.shape[0]
+    eta = np.ascontiguousarray(eta, dtype=np.float64).reshape(N, -1); nz = eta.shape[1]
+    theta = np.zeros(ny * nz)
+    rc = lib().od_oracle_least_squares(N, ny, nz, _p(fz), _p(feta), _p(eta), _p(theta))
+    return rc, theta.reshape(nz, ny).T   # reshape(θ, ny, nz) column-major
+
+
+def num_threads():
+    return lib().od_oracle_num_threads()

@@ -1,0 +1,52 @@
+"""Shared helpers of the parity tests: per-model configs and the comparison rule.
+
+Tolerances (BASELINE.json north_star): |q3 − oracle| ≤ 1e-8, |∂q3/∂(q1,q2,u) − oracle| ≤ 1e-6, fp64.
+A sample takes part in the comparison when both sides report a converged solve and the oracle's own decision margin says the
+iterate sequence is not decided by rounding noise (oracle/ip.hpp `margin`); the excluded fraction is asserted to be small.
+"""
+import numpy as np
+
+from optimization_dynamics_b200 import workloads as W
+
+Q3_TOL = 1e-8
+GRAD_TOL = 1e-6
+MARGIN_MIN = 1e-6
+
+# name → (workload generator, h, κ_eval, κ_grad, friction, model attribute in the package)
+CONFIGS = {
+    "hopper": (W.hopper_batch, 0.05, 1e-4, 1e-3, None, "hopper"),                                  # examples/hopper.jl:12-13,42
+    "acrobot_impact": (W.acrobot_batch, 0.05, 1e-4, 1e-3, None, "acrobot_impact"),                 # examples/acrobot.jl:15-23
+    "acrobot_nominal": (W.acrobot_batch, 0.05, 1e-4, 1e-3, None, "acrobot_nominal"),
+    "cartpole_friction": (W.cartpole_batch, 0.05, 1e-4, 1e-3, [0.35, 0.35], "cartpole_friction"),  # examples/cartpole.jl:15-21
+    "cartpole_frictionless": (W.cartpole_batch, 0.05, 1e-4, 1e-3, None, "cartpole_frictionless"),
+    "planar_push": (W.planar_push_batch, 0.1, 1e-4, 1e-2, None, "planarpush"),                     # examples/planar_push.jl:18-22
+}
+
+
+def oracle_pair(O, name, q1, q2, u):
+    gen, h, ke, kg, fric, _ = CONFIGS[name]
+    e = O.step_batch(name, q1, q2, u, h, ke, False, fric=fric)
+    g = O.step_batch(name, q1, q2, u, h, kg, True, fric=fric)
+    return e, g
+
+
+def compare(name, e, g, q3, d1, d2, du, st_eval, st_grad, min_fraction=0.97, grad_outlier_fraction=0.0):
+    """d1,d2,du are [B,nq,ncol] (row = q3 component); oracle blocks are column-major [B,ncol,nq]."""
+    B = q3.shape[0]
+    # > 30 iterations = Newton wandering far from the solution: rounding differences are amplified at every step (chaotic), so the
+    # final iterate is not reproducible across implementations of the same algorithm
+    ok_e = (e["status"] == 0) & (st_eval == 0) & (e["margin"] > MARGIN_MIN) & (e["iters"] <= 30)
+    ok_g = (g["status"] == 0) & (st_grad == 0) & (g["margin"] > MARGIN_MIN) & (g["ift_spread"] < 1e-8) & (g["iters"] <= 30)
+    assert ok_e.mean() >= min_fraction, "%s: only %.3f of eval solves comparable" % (name, ok_e.mean())
+    assert ok_g.mean() >= min_fraction, "%s: only %.3f of grad solves comparable" % (name, ok_g.mean())
+    # status must agree except on rounding-fragile samples
+    assert ((e["status"] != st_eval) & (e["margin"] > MARGIN_MIN)).mean() <= 0.005
+    err_q = np.abs(q3 - e["q3"])[ok_e].max()
+    assert err_q <= Q3_TOL, "%s: max|q3 − oracle| = %.3e" % (name, err_q)
+    errs = np.maximum.reduce([np.abs(d1 - g["dq1"].transpose(0, 2, 1)).reshape(B, -1).max(1),
+                              np.abs(d2 - g["dq2"].transpose(0, 2, 1)).reshape(B, -1).max(1),
+                              np.abs(du - g["du"].transpose(0, 2, 1)).reshape(B, -1).max(1)])
+    bad = ok_g & ~(errs <= GRAD_TOL)
+    assert bad.mean() <= grad_outlier_fraction, "%s: %d of %d sensitivities off by more than %g (max %.3e)" % (
+        name, bad.sum(), B, GRAD_TOL, np.nanmax(errs[ok_g]))
+    return err_q, float(np.nanmax(errs[ok_g & ~bad])) if (ok_g & ~bad).any() else 0.0

@@ -1,0 +1,143 @@
+// TEST INFRASTRUCTURE — not part of liboptdyn_b200.so.
+// Runs the product's solver templates (csrc/contact_ip.cuh, dense_ip.cuh, rocket.cuh — the exact code the CUDA kernels
+// instantiate) on the host CPU, one problem after another, so that the CPU-only test tier (`pytest -m "not gpu"`, run in a
+// container without a GPU) can check the condensed-Newton algebra against the oracle before any GPU time is spent.
+// Built by tests/conftest.py with:  nvcc -O2 -std=c++17 -Xcompiler -fPIC -shared -o tests/_build/libhostcheck.so tests/host_check.cu
+#include <string.h>
+#include "../optimization_dynamics_b200/csrc/rocket.cuh"
+
+using namespace od;
+
+template <class M> static void run_contact(const StepArgs& a) { double ws[ContactIP<M>::WS]; for (int i = 0; i < a.B; ++i) contact_step_one<M>(a, i, ws, 1); }
+
+extern "C" int hc_contact_step(int model, int B, const double* q1, const double* q2, const double* u, int nq, int nu, double h, const double* fric,
+                               double r_tol, double k_eval, double k_grad, int max_iter, int max_ls, int want_eval, int want_grad,
+                               const double* eta, int n_eta, double* q3, double* dq1, double* dq2, double* du, int* status, int* iters) {
+    StepArgs a; memset(&a, 0, sizeof(a));
+    a.B = B; a.q1 = q1; a.q2 = q2; a.u = u; a.in_stride_q = nq; a.in_stride_u = nu;
+    a.q3 = q3; a.dq1 = want_grad ? dq1 : nullptr; a.dq2 = dq2; a.du = du;
+    a.out_stride_q3 = nq; a.out_stride_dq = nq * nq; a.out_stride_du = nq * nu;
+    a.status = status; a.iters = iters; a.h = h; a.want_eval = want_eval; a.want_grad = want_grad; a.eta = eta; a.n_eta = n_eta;
+    for (int k = 0; k < 4; ++k) a.fric[k] = fric ? fric[k] : 0.0;
+    a.opts.r_tol = r_tol; a.opts.kappa_eval_tol = k_eval; a.opts.kappa_grad_tol = k_grad; a.opts.ls_scale = 0.5; a.opts.max_iter = max_iter; a.opts.max_ls = max_ls;
+    switch (model) {
+        case 0: run_contact<AcrobotImpactModel>(a); break;
+        case 1: run_contact<AcrobotNominalModel>(a); break;
+        case 2: run_contact<CartpoleFrictionModel>(a); break;
+        case 3: run_contact<CartpoleFrictionlessModel>(a); break;
+        case 4: run_contact<PlanarPushModel>(a); break;
+        case 5: run_contact<HopperModel>(a); break;
+        default: return 1;
+    }
+    return 0;
+}
+
+extern "C" int hc_rocket(int B, const double* x, const double* u, double h, double u_max, int proj, int want_grad, int proj_only,
+                         double* y, double* dx, double* du, double* uproj, double* duproj, int* status, int* iters) {
+    RocketArgs a; memset(&a, 0, sizeof(a));
+    a.B = B; a.x = x; a.u = u; a.y = y; a.dx = dx; a.du = du; a.uproj = uproj; a.duproj = duproj; a.status = status; a.iters = iters;
+    a.h = h; a.u_max = u_max; a.proj = proj; a.want_grad = want_grad; a.proj_only = proj_only;
+    a.opts.r_tol = 1e-8; a.opts.kappa_eval_tol = 1e-4; a.opts.kappa_grad_tol = 1e-4; a.opts.ls_scale = 0.5; a.opts.max_iter = 100; a.opts.max_ls = 25;
+    for (int i = 0; i < B; ++i) rocket_one(a, i);
+    return 0;
+}
+
+// residual blocks [d | rs | rpsi | rv | rgam | rc0 | rc1] and the condensed Newton direction for r at z (oracle z ordering q,γ,s,ψ,b,sψ,sb)
+template <class M> static void resid_t(const double* zz, const double* th, double* out, double* dir) {
+    typedef ContactIP<M> IP;
+    typename IP::Z z; typename IP::R r; double rv, kv;
+    const double* p = zz;
+    for (int i = 0; i < M::NQ; ++i) z.q[i] = *p++;
+    for (int i = 0; i < M::NC; ++i) z.gam[i] = *p++;
+    for (int i = 0; i < M::NC; ++i) z.s[i] = *p++;
+    for (int i = 0; i < M::NP; ++i) z.psi[i] = *p++;
+    for (int i = 0; i < M::NB; ++i) z.b[i] = *p++;
+    for (int i = 0; i < M::NP; ++i) z.spsi[i] = *p++;
+    for (int i = 0; i < M::NB; ++i) z.sb[i] = *p++;
+    IP::residual(z, th, r, rv, kv);
+    double* o = out;
+    for (int i = 0; i < M::NQ; ++i) *o++ = r.d[i];
+    for (int i = 0; i < M::NC; ++i) *o++ = r.rs[i];
+    for (int i = 0; i < M::NP; ++i) *o++ = r.rpsi[i];
+    for (int i = 0; i < M::NB; ++i) *o++ = r.rv[i];
+    for (int i = 0; i < M::NC; ++i) *o++ = r.rgam[i];
+    for (int i = 0; i < M::NP; ++i) *o++ = r.rc0[i];
+    for (int i = 0; i < M::NB; ++i) *o++ = r.rc1[i];
+    typename IP::Lin L; typename IP::Z D; double ws[IP::WS];
+    L.ws = ws; L.stride = 1;
+    IP::linearize(z, th, L);
+    IP::solve(L, z, r, D);
+    o = dir;
+    for (int i = 0; i < M::NQ; ++i) *o++ = D.q[i];
+    for (int i = 0; i < M::NC; ++i) *o++ = D.gam[i];
+    for (int i = 0; i < M::NC; ++i) *o++ = D.s[i];
+    for (int i = 0; i < M::NP; ++i) *o++ = D.psi[i];
+    for (int i = 0; i < M::NB; ++i) *o++ = D.b[i];
+    for (int i = 0; i < M::NP; ++i) *o++ = D.spsi[i];
+    for (int i = 0; i < M::NB; ++i) *o++ = D.sb[i];
+}
+extern "C" int hc_contact_residual(int model, const double* z, const double* th, double* out, double* dir) {
+    switch (model) {
+        case 0: resid_t<AcrobotImpactModel>(z, th, out, dir); break;
+        case 1: resid_t<AcrobotNominalModel>(z, th, out, dir); break;
+        case 2: resid_t<CartpoleFrictionModel>(z, th, out, dir); break;
+        case 3: resid_t<CartpoleFrictionlessModel>(z, th, out, dir); break;
+        case 4: resid_t<PlanarPushModel>(z, th, out, dir); break;
+        case 5: resid_t<HopperModel>(z, th, out, dir); break;
+        default: return 1;
+    }
+    return 0;
+}
+
+// IFT sensitivities of the product code at a given z (oracle ordering)
+template <class M> static void sens_t(const double* zz, const double* th, double* dq1, double* dq2, double* du) {
+    typedef ContactIP<M> IP;
+    typename IP::Z z;
+    const double* p = zz;
+    for (int i = 0; i < M::NQ; ++i) z.q[i] = *p++;
+    for (int i = 0; i < M::NC; ++i) z.gam[i] = *p++;
+    for (int i = 0; i < M::NC; ++i) z.s[i] = *p++;
+    for (int i = 0; i < M::NP; ++i) z.psi[i] = *p++;
+    for (int i = 0; i < M::NB; ++i) z.b[i] = *p++;
+    for (int i = 0; i < M::NP; ++i) z.spsi[i] = *p++;
+    for (int i = 0; i < M::NB; ++i) z.sb[i] = *p++;
+    typename IP::Lin L; double ws[IP::WS];
+    L.ws = ws; L.stride = 1;
+    IP::linearize(z, th, L);
+    IP::sensitivities(L, z, th, dq1, dq2, du);
+}
+extern "C" int hc_contact_sens(int model, const double* z, const double* th, double* dq1, double* dq2, double* du) {
+    switch (model) {
+        case 0: sens_t<AcrobotImpactModel>(z, th, dq1, dq2, du); break;
+        case 2: sens_t<CartpoleFrictionModel>(z, th, dq1, dq2, du); break;
+        case 4: sens_t<PlanarPushModel>(z, th, dq1, dq2, du); break;
+        case 5: sens_t<HopperModel>(z, th, dq1, dq2, du); break;
+        default: return 1;
+    }
+    return 0;
+}
+
+template <class M> static void K_t(const double* zz, const double* th, double* Kout) {
+    typedef ContactIP<M> IP;
+    typename IP::Z z;
+    const double* p = zz;
+    for (int i = 0; i < M::NQ; ++i) z.q[i] = *p++;
+    for (int i = 0; i < M::NC; ++i) z.gam[i] = *p++;
+    for (int i = 0; i < M::NC; ++i) z.s[i] = *p++;
+    for (int i = 0; i < M::NP; ++i) z.psi[i] = *p++;
+    for (int i = 0; i < M::NB; ++i) z.b[i] = *p++;
+    for (int i = 0; i < M::NP; ++i) z.spsi[i] = *p++;
+    for (int i = 0; i < M::NB; ++i) z.sb[i] = *p++;
+    typename IP::Lin L; double ws[IP::WS];
+    L.ws = ws; L.stride = 1;
+    IP::assemble(z, th, L);
+    for (int i = 0; i < IP::NR * IP::NR; ++i) Kout[i] = ws[i];
+}
+extern "C" int hc_contact_K(int model, const double* z, const double* th, double* K) {
+    switch (model) {
+        case 4: K_t<PlanarPushModel>(z, th, K); break;
+        case 5: K_t<HopperModel>(z, th, K); break;
+        default: return 1;
+    }
+    return 0;
+}

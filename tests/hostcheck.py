@@ -1,0 +1,77 @@
+"""TEST INFRASTRUCTURE: ctypes front-end of tests/_build/libhostcheck.so (product solver templates compiled for the host CPU)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+_LIB = None
+MODELS = {"acrobot_impact": 0, "acrobot_nominal": 1, "cartpole_friction": 2, "cartpole_frictionless": 3, "planar_push": 4, "hopper": 5}
+DIMS = {"acrobot_impact": (2, 1), "acrobot_nominal": (2, 1), "cartpole_friction": (2, 1), "cartpole_frictionless": (2, 1),
+        "planar_push": (5, 2), "hopper": (4, 2)}
+
+
+def build():
+    so = os.path.join(_HERE, "_build", "libhostcheck.so")
+    csrc = os.path.join(_ROOT, "optimization_dynamics_b200", "csrc")
+    srcs = [os.path.join(_HERE, "host_check.cu")] + [os.path.join(dp, f) for dp, _, fs in os.walk(csrc) for f in fs]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
+        os.makedirs(os.path.dirname(so), exist_ok=True)
+        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC", "-shared", "-o", so,
+                               os.path.join(_HERE, "host_check.cu")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+    return _LIB
+
+
+def _p(a, t=C.c_double):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+def step(model, q1, q2, u, h, k_eval=1e-4, k_grad=1e-3, fric=None, want_eval=True, want_grad=True, eta=None, r_tol=1e-8):
+    nq, nu = DIMS[model]
+    q1 = np.ascontiguousarray(q1, dtype=np.float64).reshape(-1, nq); B0 = q1.shape[0]
+    q2 = np.ascontiguousarray(q2, dtype=np.float64).reshape(B0, nq)
+    u = np.ascontiguousarray(u, dtype=np.float64).reshape(B0, nu)
+    n_eta = 0
+    if eta is not None:
+        eta = np.ascontiguousarray(eta, dtype=np.float64); n_eta = eta.shape[0]
+    B = B0 * (n_eta + 1) if eta is not None else B0
+    fr = np.zeros(4)
+    default = {"hopper": [0.5, 0.5], "cartpole_friction": [0.1, 0.1]}.get(model)   # same defaults as od_create
+    if fric is None and default is not None:
+        fric = default
+    if fric is not None:
+        fr[:len(fric)] = fric
+    q3 = np.zeros((B, nq)); dq1 = np.zeros((B, nq, nq)); dq2 = np.zeros((B, nq, nq)); du = np.zeros((B, nu, nq))
+    st = np.zeros(B, dtype=np.int32); it = np.zeros(B, dtype=np.int32)
+    rc = lib().hc_contact_step(MODELS[model], B, _p(q1), _p(q2), _p(u), nq, nu, C.c_double(h), _p(fr), C.c_double(r_tol), C.c_double(k_eval), C.c_double(k_grad),
+                               100, 25, int(want_eval), int(want_grad), _p(eta), n_eta, _p(q3), _p(dq1), _p(dq2), _p(du), _p(st, C.c_int), _p(it, C.c_int))
+    assert rc == 0
+    return dict(q3=q3, dq1=dq1, dq2=dq2, du=du, status=st, st_eval=st & 15, st_grad=(st >> 4) & 15, it_eval=it & 0xFFFF, it_grad=(it >> 16) & 0xFFFF)
+
+
+def rocket(x, u, h, u_max, proj, want_grad=True, proj_only=False):
+    x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 12); B = x.shape[0]
+    u = np.ascontiguousarray(u, dtype=np.float64).reshape(B, 3)
+    y = np.zeros((B, 12)); dx = np.zeros((B, 12, 12)); du = np.zeros((B, 3, 12)); up = np.zeros((B, 3)); dup = np.zeros((B, 3, 3))
+    st = np.zeros(B, dtype=np.int32); it = np.zeros(B, dtype=np.int32)
+    rc = lib().hc_rocket(B, _p(x), _p(u), C.c_double(h), C.c_double(u_max), int(proj), int(want_grad), int(proj_only), _p(y), _p(dx), _p(du), _p(up), _p(dup),
+                         _p(st, C.c_int), _p(it, C.c_int))
+    assert rc == 0
+    return dict(y=y, dx=dx, du=du, uproj=up, duproj=dup, status=st, iters=it)
+
+
+def residual_and_direction(model, z, th):
+    """Block residual [d|rs|rpsi|rv|rgam|rc0|rc1] at κ=0 and the condensed Newton direction rz⁻¹ r (oracle z ordering)."""
+    z = np.ascontiguousarray(z, dtype=np.float64); th = np.ascontiguousarray(th, dtype=np.float64)
+    out = np.zeros(len(z)); d = np.zeros(len(z))
+    assert lib().hc_contact_residual(MODELS[model], _p(z), _p(th), _p(out), _p(d)) == 0
+    return out, d

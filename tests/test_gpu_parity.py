@@ -1,0 +1,180 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C ABI (ctypes → liboptdyn_b200.so), against the oracle on identical
+seeded inputs, against the committed golden vectors, and through size-independent properties at BASELINE.json's full sizes."""
+import os
+
+import numpy as np
+import pytest
+
+from common import CONFIGS, compare, oracle_pair, Q3_TOL, GRAD_TOL
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def od(built):
+    import optimization_dynamics_b200 as od
+    return od
+
+
+@pytest.fixture(scope="module")
+def O(built):
+    from oracle import oracle as O
+    return O
+
+
+def make_dyn(od, name):
+    gen, h, ke, kg, fric, attr = CONFIGS[name]
+    model = getattr(od, attr)
+    if fric is not None:
+        model.friction[:] = fric                    # examples/cartpole.jl:21 mutates the model after construction
+    return od.ImplicitDynamics(model, h, r_tol=1e-8, κ_eval_tol=ke, κ_grad_tol=kg)
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_step_and_gradients_match_oracle(od, O, name):
+    gen, h, ke, kg, fric, _ = CONFIGS[name]
+    B = 4096 if name == "hopper" else 1024
+    q1, q2, u = gen(B, h=h, seed=0)
+    dyn = make_dyn(od, name)
+    q3, d1, d2, du, st = dyn.step_grad_batch(q1, q2, u)
+    e, g = oracle_pair(O, name, q1, q2, u)
+    eq, eg = compare(name, e, g, q3, d1, d2, du, st & 15, (st >> 4) & 15, grad_outlier_fraction=0.01 if name == "planar_push" else 0.0)
+    print("%s: B=%d  max|q3-oracle|=%.2e  max|grad-oracle|=%.2e" % (name, B, eq, eg))
+    assert dyn.launch_count() >= 1
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_golden_vectors(od, name):
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+    dyn = make_dyn(od, name)
+    q3, d1, d2, du, st = dyn.step_grad_batch(gold["q1"], gold["q2"], gold["u"])
+    ok = (gold["status_eval"] == 0) & (gold["status_grad"] == 0) & (st == 0) & (gold["margin"] > 1e-6) & (gold["ift_spread"] < 1e-8) \
+        & (gold["iters_eval"] <= 30)
+    assert ok.mean() > 0.9
+    assert np.abs(q3 - gold["q3"])[ok].max() <= Q3_TOL
+    errs = np.maximum.reduce([np.abs(d1 - gold["dq1"].transpose(0, 2, 1)).reshape(len(st), -1).max(1),
+                              np.abs(d2 - gold["dq2"].transpose(0, 2, 1)).reshape(len(st), -1).max(1),
+                              np.abs(du - gold["du"].transpose(0, 2, 1)).reshape(len(st), -1).max(1)])
+    assert (errs[ok] > GRAD_TOL).mean() <= (0.02 if name == "planar_push" else 0.0)
+
+
+def test_f_fx_fu_mirror_the_reference_call_shapes(od, O):
+    """f / fx / fu on one (x, u), the way IterativeLQR calls them (reference src/dynamics.jl:81-128)."""
+    h = 0.05
+    q1, q2, u = od.workloads.hopper_batch(4, h=h, seed=1)
+    dyn = make_dyn(od, "hopper")
+    x = np.concatenate([q1[0], q2[0]])
+    d = np.zeros(8); dx = np.zeros((8, 8)); du = np.zeros((8, 2))
+    od.f(d, dyn, x, u[0], np.zeros(0)); od.fx(dx, dyn, x, u[0], np.zeros(0))
+    n0 = dyn.launch_count()
+    od.fu(du, dyn, x, u[0], np.zeros(0))
+    assert dyn.launch_count() == n0                       # fu reuses fx's solve (the reference solves again)
+    e = O.step_batch("hopper", q1[:1], q2[:1], u[:1], h, 1e-4, False)
+    g = O.step_batch("hopper", q1[:1], q2[:1], u[:1], h, 1e-3, True)
+    assert np.array_equal(d[:4], q2[0]) and np.abs(d[4:] - e["q3"][0]).max() <= Q3_TOL
+    assert np.array_equal(dx[:4, 4:], np.eye(4)) and not dx[:4, :4].any()
+    assert np.abs(dx[4:, :4] - g["dq1"][0].T).max() <= GRAD_TOL and np.abs(dx[4:, 4:] - g["dq2"][0].T).max() <= GRAD_TOL
+    assert not du[:4].any() and np.abs(du[4:] - g["du"][0].T).max() <= GRAD_TOL
+    assert [len(v) for v in od.state_to_configuration([x, d])] == [4, 4, 4]
+
+
+def test_full_size_properties_hopper_4096(od):
+    """BASELINE.json headline size: determinism, batch-permutation equivariance, packed == separate arrays, f-only == f+gradient."""
+    h = 0.05
+    q1, q2, u = od.workloads.hopper_batch(4096, h=h, seed=0)
+    dyn = make_dyn(od, "hopper")
+    q3, d1, d2, du, st = dyn.step_grad_batch(q1, q2, u)
+    q3b, d1b, d2b, dub, stb = dyn.step_grad_batch(q1, q2, u)
+    assert np.array_equal(q3, q3b) and np.array_equal(d1, d1b) and np.array_equal(du, dub) and np.array_equal(st, stb)
+    perm = np.random.default_rng(0).permutation(4096)
+    q3p, d1p, d2p, dup, stp = dyn.step_grad_batch(q1[perm], q2[perm], u[perm])
+    assert np.array_equal(q3p, q3[perm]) and np.array_equal(d2p, d2[perm]) and np.array_equal(stp, st[perm])
+    out, st2 = dyn.step_grad_packed(np.concatenate([q1, q2, u], axis=1))
+    from optimization_dynamics_b200.device import unpack_outputs
+    a, b1, b2, c = unpack_outputs(out, 4, 2)
+    assert np.array_equal(a, q3) and np.array_equal(b1, d1) and np.array_equal(b2, d2) and np.array_equal(c, du) and np.array_equal(st2, st)
+    q3only, st3 = dyn.step_batch(q1, q2, u)
+    assert np.array_equal(q3only, q3) and np.array_equal(st3, st & 15)
+    assert (st == 0).mean() > 0.99
+    # physics sanity on the whole batch: feet never end below the ground, leg length within its limits (to κ-level tolerance)
+    foot_z = q3[:, 1] - q3[:, 3] * np.cos(q3[:, 2])
+    ok = st == 0
+    assert (foot_z[ok] >= 0.05 - 1e-6).all() and (q3[ok, 3] >= 0.25 - 1e-6).all() and (q3[ok, 3] <= 1.0 + 1e-6).all()
+
+
+def test_edge_cases(od):
+    dyn = make_dyn(od, "hopper")
+    q3, st = dyn.step_batch(np.zeros((0, 4)), np.zeros((0, 4)), np.zeros((0, 2)))          # empty batch
+    assert q3.shape == (0, 4) and st.shape == (0,)
+    for B in (1, 31, 33):                                                                   # ragged (not a multiple of the block size)
+        q1, q2, u = od.workloads.hopper_batch(B, seed=B)
+        full = dyn.step_grad_batch(q1, q2, u)
+        one = dyn.step_grad_batch(q1[-1:], q2[-1:], u[-1:])
+        assert np.array_equal(full[0][-1], one[0][0]) and np.array_equal(full[1][-1], one[1][0])
+    # a non-finite input must be flagged, never silently "converged"
+    q1, q2, u = od.workloads.hopper_batch(8, seed=1)
+    q2[3, 1] = np.nan
+    _, _, _, _, st = dyn.step_grad_batch(q1, q2, u)
+    assert (st[3] & 15) == 2 and ((st[3] >> 4) & 15) == 2 and (np.delete(st, 3) == 0).all()
+    with pytest.raises(RuntimeError):
+        od.ImplicitDynamics(od.hopper, -1.0)
+
+
+def test_gradient_bundle_matches_oracle_and_ift(od, O):
+    """cfg 2 of BASELINE.json: cartpole μ=0.35, bundle N=64 — (N+1)·B solves in one launch, closed-form fit."""
+    name = "cartpole_friction"
+    gen, h, ke, kg, fric, _ = CONFIGS[name]
+    q1, q2, u = gen(50, h=h, seed=4)
+    dyn = make_dyn(od, name)
+    eta = od.workloads.bundle_perturbations(5, N=64, seed=0)
+    gb = od.GradientBundle(dyn.model, eta=eta)
+    dz, st = od.gradient_batch(dyn, gb, q1, q2, u)
+    ob = O.bundle_batch(name, eta, q1, q2, u, h, ke, fric=fric)
+    ok = (st == 0) & (ob["status"] == 0)
+    assert ok.mean() > 0.95
+    assert np.abs(dz - ob["dz"].transpose(0, 2, 1))[ok].max() < 1e-5      # finite-difference quotients amplify 1e-12 by 1/ε = 1e4
+    # fx_gb / fu_gb scatter (reference src/gradient_bundle.jl:109-147)
+    dyn.info = gb
+    x = np.concatenate([q1[0], q2[0]]); dx = np.zeros((4, 4)); du = np.zeros((4, 1))
+    od.fx_gb(dx, dyn, x, u[0], None); od.fu_gb(du, dyn, x, u[0], None)
+    assert np.array_equal(dx[:2, 2:], np.eye(2)) and np.allclose(dx[2:, :2], dz[0][:, :2]) and np.allclose(du[2:, 0], dz[0][:, 4])
+    with pytest.raises(RuntimeError, match="singular"):
+        bad = np.zeros((8, 5)); bad[:, 0] = 1e-4
+        od.gradient_batch(dyn, od.GradientBundle(dyn.model, eta=bad), q1, q2, u)
+
+
+@pytest.mark.parametrize("proj", [False, True])
+def test_rocket_matches_oracle(od, O, proj):
+    x, u = od.workloads.rocket_batch(1024, seed=0)
+    info = od.RocketInfo(od.rocket, 12.5, 0.05)
+    y, dx, du, st = info.step_batch(x, u, proj)
+    o = O.rocket_batch(x, u, 0.05, 12.5, proj, True)
+    ok = (o["status"] == 0) & (st == 0) & (o["margin"] > 1e-6)
+    assert ok.mean() > 0.9
+    assert np.abs(y - o["y"])[ok].max() <= Q3_TOL
+    assert np.abs(dx - o["dx"].transpose(0, 2, 1))[ok].max() <= GRAD_TOL and np.abs(du - o["du"].transpose(0, 2, 1))[ok].max() <= GRAD_TOL
+    if proj:
+        up, dp, stp = info.projection_batch(u)
+        assert (np.hypot(up[:, 0], up[:, 1]) <= up[:, 2] + 1e-6).all() and (up[:, 2] <= 12.5 + 1e-6).all()     # examples/rocket.jl:151
+        d = np.zeros(12); od.f_rocket_proj(d, info, x[0], u[0], None)
+        assert np.array_equal(d, y[0])
+    gold = np.load(os.path.join(GOLDEN, "rocket_proj.npz" if proj else "rocket.npz"))
+    yg, dxg, dug, stg = info.step_batch(gold["x"], gold["u"], proj)
+    okg = (gold["status"] == 0) & (stg == 0) & (gold["margin"] > 1e-6)
+    assert np.abs(yg - gold["y"])[okg].max() <= Q3_TOL and np.abs(dxg - gold["dx"].transpose(0, 2, 1))[okg].max() <= GRAD_TOL
+
+
+def test_device_resident_packed_path_and_launch_accounting(od):
+    import torch
+    from optimization_dynamics_b200.device import DeviceStepper
+    q1, q2, u = od.workloads.hopper_batch(4096, seed=0)
+    dyn = make_dyn(od, "hopper")
+    ref, st_ref = dyn.step_grad_packed(np.concatenate([q1, q2, u], axis=1))
+    stepper = DeviceStepper(dyn)
+    xin = torch.from_numpy(np.concatenate([q1, q2, u], axis=1)).cuda()
+    n0 = dyn.launch_count()
+    out, st = stepper.step_grad_packed(xin)
+    torch.cuda.synchronize()
+    assert dyn.launch_count() == n0 + 1
+    assert np.array_equal(out.cpu().numpy(), ref) and np.array_equal(st.cpu().numpy(), st_ref)

@@ -1,0 +1,136 @@
+"""CPU tier: (1) the product's solver templates, compiled for the host by tests/host_check.cu, against the oracle — the same
+template code the CUDA kernels instantiate, so the reduced-system algebra is checked without a GPU; (2) the C ABI loads and
+exports every symbol include/optdyn_b200.h declares and fails loudly without a CUDA device; (3) host-side helpers."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import hostcheck as H
+from oracle import oracle as O
+from optimization_dynamics_b200 import workloads as W
+from common import CONFIGS, compare, oracle_pair
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_solver_templates_match_oracle(name):
+    gen, h, ke, kg, fric, _ = CONFIGS[name]
+    B = 1024 if name != "planar_push" else 512
+    q1, q2, u = gen(B, h=h, seed=1)
+    e, g = oracle_pair(O, name, q1, q2, u)
+    r = H.step(name, q1, q2, u, h, ke, kg, fric=fric)
+    tr = lambda a: a.transpose(0, 2, 1)
+    eq, eg = compare(name, e, g, r["q3"], tr(r["dq1"]), tr(r["dq2"]), tr(r["du"]), r["st_eval"], r["st_grad"],
+                     grad_outlier_fraction=0.01 if name == "planar_push" else 0.0)
+    # same iterate sequence ⇒ same iteration counts on every comparable sample
+    ok = (e["status"] == 0) & (r["st_eval"] == 0) & (e["margin"] > 1e-6)
+    assert (e["iters"][ok] != r["it_eval"][ok]).mean() <= 0.002
+
+
+def test_eval_only_and_grad_only_paths_agree_with_combined():
+    q1, q2, u = W.hopper_batch(128, seed=9)
+    both = H.step("hopper", q1, q2, u, 0.05)
+    ev = H.step("hopper", q1, q2, u, 0.05, want_grad=False)
+    gr = H.step("hopper", q1, q2, u, 0.05, want_eval=False)
+    assert np.array_equal(both["q3"], ev["q3"])
+    assert np.array_equal(both["dq1"], gr["dq1"]) and np.array_equal(both["du"], gr["du"])
+
+
+def test_residual_blocks_and_newton_direction_match_dense_oracle():
+    rng = np.random.default_rng(1)
+    for _ in range(10):
+        z = np.concatenate([[0.1, 0.6, 0.2, 0.5] + 0.1 * rng.normal(size=4), rng.uniform(0.5, 1.5, 8), rng.uniform(1.0, 1.5, 2), rng.uniform(-0.3, 0.3, 2),
+                            rng.uniform(1.0, 1.5, 2), rng.uniform(-0.3, 0.3, 2)])
+        th = np.concatenate([[0.08, 0.61, 0.18, 0.52], [0.09, 0.6, 0.19, 0.51], rng.normal(size=2), [0.5, 0.6], [0.05]])
+        r, rz, rth = O.residual("hopper", z, th)
+        blocks, d = H.residual_and_direction("hopper", z, th)
+        perm = list(range(16)) + [16, 18, 17, 19]       # oracle interleaves (cone row 0, cone row 1) per cone
+        assert np.abs(blocks - r[perm]).max() < 1e-13
+        assert np.abs(d - np.linalg.solve(rz, r)).max() < 1e-11
+
+
+@pytest.mark.parametrize("proj", [False, True])
+def test_rocket_templates_match_oracle(proj):
+    x, u = W.rocket_batch(512, seed=1)
+    o = O.rocket_batch(x, u, 0.05, 12.5, proj, True)
+    r = H.rocket(x, u, 0.05, 12.5, proj)
+    ok = (o["status"] == 0) & (r["status"] == 0) & (o["margin"] > 1e-6)
+    assert ok.mean() > 0.9
+    assert np.abs(o["y"] - r["y"])[ok].max() < 1e-8
+    assert np.abs(o["dx"] - r["dx"])[ok].max() < 1e-6 and np.abs(o["du"] - r["du"])[ok].max() < 1e-6
+
+
+@pytest.mark.parametrize("name", ["hopper", "cartpole_friction"])
+def test_bundle_closed_form_matches_reference_newton_fit(name):
+    """(N+1)·B perturbed steps + normal equations == the oracle's restatement of gradient! + LeastSquares.update!."""
+    gen, h, ke, kg, fric, _ = CONFIGS[name]
+    nq, nu = H.DIMS[name]
+    ncol = 2 * nq + nu
+    q1, q2, u = gen(12, h=h, seed=3)
+    eta = W.bundle_perturbations(ncol, N=64, seed=1)
+    ob = O.bundle_batch(name, eta, q1, q2, u, h, ke, fric=fric)
+    r = H.step(name, q1, q2, u, h, ke, kg, fric=fric, want_grad=False, eta=eta)
+    f = r["q3"].reshape(12, 65, nq)
+    M = np.einsum("bki,kj->bij", f[:, 1:] - f[:, :1], eta) @ np.linalg.inv(eta.T @ eta)
+    assert (ob["status"] == 0).all()
+    assert np.abs(M - ob["dz"].transpose(0, 2, 1)).max() < 1e-6
+
+
+def test_c_abi_exports_every_declared_symbol(built):
+    from optimization_dynamics_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "optdyn_b200.h")).read()
+    declared = set(re.findall(r"\b(od_[a-z_0-9]+)\s*\(", hdr)) - {"od_handle", "od_options", "od_model"}
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    L = C.CDLL(_lib.SO_PATH)
+    for s in declared:
+        assert hasattr(L, s), s
+    L2 = _lib.lib()
+    nq, nu, nz, nth = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    for mid, want in ((5, (4, 2, 20, 13)), (4, (5, 2, 35, 13)), (2, (2, 1, 10, 8)), (0, (2, 1, 6, 6)), (6, (12, 3, 12, 16))):
+        assert L2.od_model_dims(mid, C.byref(nq), C.byref(nu), C.byref(nz), C.byref(nth)) == 0
+        assert (nq.value, nu.value, nz.value, nth.value) == want
+    assert L2.od_model_dims(99, None, None, None, None) != 0
+    o = _lib.od_options()
+    assert L2.od_default_options(5, C.byref(o)) == 0 and o.r_tol == 1e-8 and o.max_ls == 25 and o.kappa_grad_tol == 1e-3
+
+
+def test_no_cpu_fallback(built):
+    """Without a CUDA device construction must raise — the product never computes on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import optimization_dynamics_b200 as od
+    with pytest.raises(RuntimeError, match="no CUDA device|CUDA"):
+        od.ImplicitDynamics(od.hopper, 0.05, κ_eval_tol=1e-4, κ_grad_tol=1e-3)
+    with pytest.raises(RuntimeError):
+        od.RocketInfo(od.rocket, 12.5, 0.05)
+
+
+def test_product_package_never_imports_oracle():
+    pkg = os.path.join(ROOT, "optimization_dynamics_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f), errors="ignore").read()
+                assert "oracle" not in src.replace("against the oracle", "").replace("the oracle", "").lower() or f in ("contact_ip.cuh",), (dp, f)
+
+
+def test_shard_ranges_cover_the_batch():
+    from optimization_dynamics_b200.device import shard_range, shard_sizes
+    for B in (0, 1, 7, 4096, 4097):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(B, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert max(shard_sizes(B, w)) - min(shard_sizes(B, w)) <= 1
+
+
+def test_state_to_configuration():
+    from optimization_dynamics_b200 import state_to_configuration
+    x = [np.array([1.0, 2.0, 3.0, 4.0]), np.array([3.0, 4.0, 5.0, 6.0])]
+    q = state_to_configuration(x)
+    assert [list(v) for v in q] == [[1.0, 2.0], [3.0, 4.0], [5.0, 6.0]]

@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""Build-time code generator: symbolic model definitions -> CUDA device functions.
+
+Successor of the reference's Symbolics.jl code generation (reference deps/build.jl:27-49, src/models/*/codegen.jl): each
+model's residual is written down symbolically (sympy), differentiated exactly, common sub-expressions are eliminated and the
+result is printed as straight-line `__device__` code under optimization_dynamics_b200/csrc/gen/.  Unlike the reference,
+which generates dense r / rz / rθ, the contact models are emitted in *block* form for the condensed Newton solver
+(csrc/contact_ip.cuh):
+
+    d(q, γ, b; θ)   dynamics rows                ϕ(q)      signed distances        ψ̂(γ; θ)  friction-cone radius targets
+    vT(q; θ)        tangential velocities
+    D = ∂d/∂q   Eγ = ∂d/∂γ   Eb = ∂d/∂b   N = ∂ϕ/∂q   V = ∂vT/∂q   Mψ = ∂ψ̂/∂γ        (jac)
+    Dθ = ∂d/∂θ'   Vθ = ∂vT/∂θ'   with θ' = (q1, q2, u) — the columns f/fx/fu return    (jacth)
+
+Run:  python tools/codegen/gen_models.py            (regenerates every header; output is committed)
+"""
+import os
+import sys
+import time
+
+import sympy as sp
+from sympy.printing.c import C99CodePrinter
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "optimization_dynamics_b200", "csrc", "gen")
+
+
+class Printer(C99CodePrinter):
+    def _print_Pow(self, expr):
+        b, e = expr.base, expr.exp
+        if e.is_Integer:
+            n = int(e)
+            if n == -1:
+                return "(1.0/(%s))" % self._print(b)
+            if 0 < n <= 12:
+                s = self.parenthesize(b, 1000)
+                return "(" + "*".join([s] * n) + ")"
+            if -12 <= n < 0:
+                s = self.parenthesize(b, 1000)
+                return "(1.0/(" + "*".join([s] * (-n)) + "))"
+        if e == sp.Rational(1, 2):
+            return "sqrt(%s)" % self._print(b)
+        if e == -sp.Rational(1, 2):
+            return "rsqrt_d(%s)" % self._print(b)
+        return "pow(%s, %s)" % (self._print(b), self._print(sp.Float(e) if e.is_Rational else e))
+
+    def _print_Rational(self, expr):
+        return "(%d.0/%d.0)" % (expr.p, expr.q)
+
+    def _print_Float(self, expr):
+        return repr(float(expr))
+
+    def _print_Integer(self, expr):
+        return "%d.0" % int(expr)
+
+
+PR = Printer()
+
+
+def vec(name, n):
+    return [sp.Symbol("%s%d" % (name, i), real=True) for i in range(n)]
+
+
+def emit_function(fname, inputs, outputs, doc=""):
+    """inputs: list of (array_name, symbols); outputs: list of (array_name, sympy Matrix/list flattened row-major)."""
+    exprs, slots = [], []
+    for oname, vals in outputs:
+        flat = list(vals)
+        for i, e in enumerate(flat):
+            exprs.append(sp.sympify(e))
+            slots.append((oname, i))
+    t0 = time.time()
+    repl, red = sp.cse(exprs, symbols=sp.numbered_symbols("x"), optimizations="basic", order="none")
+    lines = []
+    used = set()
+    for e in list(red) + [r for _, r in repl]:
+        used |= e.free_symbols
+    args = ", ".join(["const double* __restrict__ %s" % n for n, _ in inputs] + ["double* __restrict__ %s" % n for n, _ in outputs])
+    lines.append("// %s" % doc if doc else "")
+    lines.append("OD_HD void %s(%s) {" % (fname, args))
+    for aname, syms in inputs:
+        for i, s in enumerate(syms):
+            if s in used:
+                lines.append("    const double %s = %s[%d];" % (s.name, aname, i))
+    for s, e in repl:
+        lines.append("    const double %s = %s;" % (s.name, PR.doprint(e)))
+    for (oname, i), e in zip(slots, red):
+        lines.append("    %s[%d] = %s;" % (oname, i, PR.doprint(e)))
+    lines.append("}")
+    nops = sum(sp.count_ops(e) for _, e in repl) + sum(sp.count_ops(e) for e in red)
+    sys.stderr.write("  %-28s %4d temporaries %6d ops  (%.1fs)\n" % (fname, len(repl), nops, time.time() - t0))
+    return "\n".join(lines) + "\n", nops
+
+
+def variational(Mv, C, q0, q1, q2, h):
+    """d = h/2 D1L1 + D2L1 + h/2 D1L2 − D2L2, D1L = −C(q,v), D2L = M(q) v   (reference src/models/cartpole/model.jl:53-63)."""
+    n = len(q0)
+    qm1 = [(q0[i] + q1[i]) / 2 for i in range(n)]
+    vm1 = [(q1[i] - q0[i]) / h for i in range(n)]
+    qm2 = [(q1[i] + q2[i]) / 2 for i in range(n)]
+    vm2 = [(q2[i] - q1[i]) / h for i in range(n)]
+    C1, C2 = C(qm1, vm1), C(qm2, vm2)
+    p1, p2 = Mv(qm1, vm1), Mv(qm2, vm2)
+    return [h / 2 * (-C1[i]) + p1[i] + h / 2 * (-C2[i]) - p2[i] for i in range(n)], qm2, vm2
+
+
+def lagrangian_MC(L, q, qd):
+    """M = ∂²L/∂q̇², C = (∂²L/∂q̇∂q) q̇ − ∂L/∂q  (RoboDojo codegen convention)."""
+    n = len(q)
+    M = sp.Matrix(n, n, lambda i, j: sp.diff(L, qd[i], qd[j]))
+    dLq = sp.Matrix([sp.diff(L, q[i]) for i in range(n)])
+    ddLqdq = sp.Matrix(n, n, lambda i, j: sp.diff(L, qd[i], q[j]))
+    C = ddLqdq * sp.Matrix(qd) - dLq
+    return sp.simplify(M), sp.simplify(C)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# model definitions: return dict(name, NQ, NU, NC, NP, NB, cone_dims, theta symbols, d, phi, psit, vT)
+# ---------------------------------------------------------------------------------------------------------------------
+def model_hopper():
+    NQ, NU, NC, NP, NB = 4, 2, 4, 2, 2
+    q, gam, b = vec("q", NQ), vec("g", NC), vec("b", NB)
+    th = vec("t", 13)
+    q0, q1, u, mu, h = th[0:4], th[4:8], th[8:10], th[10:12], th[12]
+    mb, Ib, mf, grav = 3.0, 0.75, 1.0, 9.81
+    rb, rf, lmax, lmin = 0.1, 0.05, 1.0, 0.25
+    # Lagrangian (RoboDojo hopper)
+    Q, Qd = vec("Q", 4), vec("V", 4)
+    foot = [Q[0] + Q[3] * sp.sin(Q[2]), Q[1] - Q[3] * sp.cos(Q[2])]
+    vfoot = [sum(sp.diff(foot[k], Q[i]) * Qd[i] for i in range(4)) for k in range(2)]
+    L = (sp.Rational(1, 2) * mb * (Qd[0] ** 2 + Qd[1] ** 2) + sp.Rational(1, 2) * Ib * Qd[2] ** 2
+         + sp.Rational(1, 2) * mf * (vfoot[0] ** 2 + vfoot[1] ** 2) - mb * grav * Q[1] - mf * grav * foot[1])
+    Msym, Csym = lagrangian_MC(L, Q, Qd)
+
+    def Mv(qq, vv):
+        sub = dict(zip(Q + Qd, list(qq) + list(vv)))
+        return list((Msym * sp.Matrix(Qd)).subs(sub))
+
+    def C(qq, vv):
+        sub = dict(zip(Q + Qd, list(qq) + list(vv)))
+        return list(Csym.subs(sub))
+
+    d, qm2, vm2 = variational(Mv, C, q0, q1, q, h)
+    # B(qm2)' u, B = [0 0 1 0; −sin t  cos t  0  1]
+    d[0] += -sp.sin(qm2[2]) * u[1]
+    d[1] += sp.cos(qm2[2]) * u[1]
+    d[2] += u[0]
+    d[3] += u[1]
+    st, ct = sp.sin(q[2]), sp.cos(q[2])
+    Jfx = [1, 0, q[3] * ct, st]
+    Jfz = [0, 1, q[3] * st, -ct]
+    for i in range(4):
+        d[i] += Jfx[i] * b[1] + Jfz[i] * gam[1]
+    d[0] += b[0]
+    d[1] += gam[0]
+    d[2] += rb * b[0]
+    d[3] += gam[2] - gam[3]
+    phi = [q[1] - rb, q[1] - q[3] * ct - rf, q[3] - lmin, lmax - q[3]]
+    psit = [mu[0] * gam[0], mu[1] * gam[1]]
+    v = [(q[i] - q1[i]) / h for i in range(4)]
+    vT = [v[0] + rb * v[2], sum(Jfx[i] * v[i] for i in range(4))]
+    return dict(name="hopper", NQ=NQ, NU=NU, NC=NC, NP=NP, NB=NB, cone_dims=[1, 1], NTH=13, q=q, gam=gam, b=b, th=th,
+                d=d, phi=phi, psit=psit, vT=vT)
+
+
+def _acrobot(impact):
+    NQ, NU = 2, 1
+    NC = 2 if impact else 0
+    q, gam, b = vec("q", NQ), vec("g", max(NC, 1)), vec("b", 1)
+    th = vec("t", 6)
+    q0, q1, u, h = th[0:2], th[2:4], th[4], th[5]
+    m1, J1, l1, lc1, m2, J2, l2, lc2, g = 1.0, 0.333, 1.0, 0.5, 1.0, 0.333, 1.0, 0.5, 9.81
+
+    def Mv(x, v):
+        a = J1 + J2 + m2 * l1 * l1 + 2.0 * m2 * l1 * lc2 * sp.cos(x[1])
+        bb = J2 + m2 * l1 * lc2 * sp.cos(x[1])
+        c = J2
+        return [a * v[0] + bb * v[1], bb * v[0] + c * v[1]]
+
+    def C(x, v):
+        k = m2 * l1 * lc2
+        ca, cb, cc = -2.0 * k * sp.sin(x[1]) * v[1], -1.0 * k * sp.sin(x[1]) * v[1], k * sp.sin(x[1]) * v[0]
+        ta = -1.0 * m1 * g * lc1 * sp.sin(x[0]) - m2 * g * (l1 * sp.sin(x[0]) + lc2 * sp.sin(x[0] + x[1]))
+        tb = -1.0 * m2 * g * lc2 * sp.sin(x[0] + x[1])
+        return [ca * v[0] + cb * v[1] - ta, cc * v[0] - tb]
+
+    d, qm2, vm2 = variational(Mv, C, q0, q1, q, h)
+    d[1] += u
+    for i in range(2):
+        d[i] += -h * sp.Rational(1, 2) * vm2[i]
+    phi = []
+    if impact:
+        phi = [sp.pi / 2 - q[1], q[1] + sp.pi / 2]
+        d[1] += gam[1] - gam[0]     # P' λ, P = ∂ϕ/∂q
+    return dict(name="acrobot_impact" if impact else "acrobot_nominal", NQ=NQ, NU=NU, NC=NC, NP=0, NB=0, cone_dims=[], NTH=6,
+                q=q, gam=gam, b=b, th=th, d=d, phi=phi, psit=[], vT=[])
+
+
+def _cartpole(friction):
+    NQ, NU = 2, 1
+    NP = NB = 2 if friction else 0
+    q, gam, b = vec("q", NQ), vec("g", 1), vec("b", max(NB, 1))
+    th = vec("t", 8 if friction else 6)
+    q0, q1, u = th[0:2], th[2:4], th[4]
+    h = th[7] if friction else th[5]
+    mc, mp, l, g = 1.0, 0.2, 0.5, 9.81
+
+    def Mv(x, v):
+        return [(mc + mp) * v[0] + mp * l * sp.cos(x[1]) * v[1], mp * l * sp.cos(x[1]) * v[0] + mp * l ** 2 * v[1]]
+
+    def C(x, v):
+        c12 = -1.0 * mp * v[1] * l * sp.sin(x[1])
+        return [-(c12 * v[1]), mp * g * l * sp.sin(x[1])]
+
+    d, qm2, vm2 = variational(Mv, C, q0, q1, q, h)
+    d[0] += u
+    psit, vT = [], []
+    if friction:
+        d[0] += b[0]
+        d[1] += b[1]
+        psit = [th[5] * (mp + mc) * g * h, th[6] * (mp * g * l) * h]
+        vT = [(q[0] - q1[0]) / h, (q[1] - q1[1]) / h]
+    return dict(name="cartpole_friction" if friction else "cartpole_frictionless", NQ=NQ, NU=NU, NC=0, NP=NP, NB=NB,
+                cone_dims=[1, 1] if friction else [], NTH=len(th), q=q, gam=gam, b=b, th=th, d=d, phi=[], psit=psit, vT=vT)
+
+
+def model_planar_push():
+    NQ, NU, NC, NP, NB = 5, 2, 1, 5, 9
+    q, gam, b = vec("q", NQ), vec("g", NC), vec("b", NB)
+    th = vec("t", 13)
+    q0, q1, u, h = th[0:5], th[5:10], th[10:12], th[12]
+    r_dim, mu_s, mu_p, grav, m_b, m_p = 0.1, 0.5, 0.5, 9.81, 1.0, 10.0
+    inertia = 1.0 / 12.0 * m_b * ((2.0 * r_dim) ** 2 + (2.0 * r_dim) ** 2)
+    c, s = sp.cos(-q[2]), sp.sin(-q[2])
+    dx, dy = q[3] - q[0], q[4] - q[1]
+    D1, D2 = c * dx - s * dy, s * dx + c * dy
+    phi = (D1 ** 10 + D2 ** 10) ** sp.Rational(1, 10) - r_dim
+    N = [sp.diff(phi, q[i]) for i in range(5)]
+    cc = [(r_dim, r_dim), (-r_dim, r_dim), (r_dim, -r_dim), (-r_dim, -r_dim)]
+    ct, st = sp.cos(q[2]), sp.sin(q[2])
+    P = []
+    for (cx, cy) in cc:
+        px = q[0] + ct * cx - st * cy
+        py = q[1] + st * cx + ct * cy
+        P.append([sp.diff(px, q[i]) for i in range(5)])
+        P.append([sp.diff(py, q[i]) for i in range(5)])
+    nn = sp.sqrt(N[3] ** 2 + N[4] ** 2)
+    n1, n2 = N[3] / nn, N[4] / nn
+    t1, t2 = -n2, n1
+    r1, r2 = q[3] - q[0], q[4] - q[1]
+    m = r1 * t2 - r2 * t1
+    P.append([t1, t2, m, -t1, -t2])
+    Md = [m_b, m_b, inertia, m_p, m_p]
+    d = []
+    for i in range(5):
+        vm1, vm2 = (q1[i] - q0[i]) / h, (q[i] - q1[i]) / h
+        e = Md[i] * vm1 - Md[i] * vm2
+        if i == 3:
+            e += u[0]
+        if i == 4:
+            e += u[1]
+        e += N[i] * gam[0] + sum(P[k][i] * b[k] for k in range(9))
+        d.append(e)
+    psit = [mu_s * m_b * grav * h * sp.Rational(1, 4)] * 4 + [mu_p * gam[0]]
+    vT = [sum(P[k][j] * (q[j] - q1[j]) for j in range(5)) / h for k in range(9)]
+    return dict(name="planar_push", NQ=NQ, NU=NU, NC=NC, NP=NP, NB=NB, cone_dims=[2, 2, 2, 2, 1], NTH=13, q=q, gam=gam, b=b, th=th,
+                d=d, phi=[phi], psit=psit, vT=vT)
+
+
+def gen_contact(m):
+    NQ, NU, NC, NP, NB = m["NQ"], m["NU"], m["NC"], m["NP"], m["NB"]
+    q, gam, b, th = m["q"], m["gam"], m["b"], m["th"]
+    thp = th[0:2 * NQ + NU]
+    ins = [("q", q), ("gam", gam), ("b", b), ("th", th)]
+    d, phi, psit, vT = sp.Matrix(m["d"]), sp.Matrix(m["phi"]), sp.Matrix(m["psit"]), sp.Matrix(m["vT"])
+
+    def J(f, x, n):
+        return list(f.jacobian(sp.Matrix(x[:n]))) if (len(f) and n) else []
+
+    out = ["// GENERATED by tools/codegen/gen_models.py — do not edit.  Model: %s" % m["name"],
+           "// Block-form residual pieces of the contact-implicit step (see csrc/contact_ip.cuh for the layout).",
+           "#pragma once", "namespace od { namespace gen_%s {" % m["name"],
+           "constexpr int NQ = %d, NU = %d, NC = %d, NP = %d, NB = %d, NTH = %d;" % (NQ, NU, NC, NP, NB, m["NTH"]), ""]
+    total = {}
+    src, total["eq"] = emit_function("eq", ins, [("d", d), ("phi", phi), ("psit", psit), ("vT", vT)],
+                                     "d(q,γ,b;θ), ϕ(q), ψ̂(γ;θ), vT(q;θ)")
+    out.append(src)
+    src, total["jac"] = emit_function("jac", ins, [("D", J(d, q, NQ)), ("Eg", J(d, gam, NC)), ("Eb", J(d, b, NB)), ("N", J(phi, q, NQ)),
+                                                   ("V", J(vT, q, NQ)), ("Mpsi", J(psit, gam, NC))],
+                                      "row-major D[NQ×NQ], Eg[NQ×NC], Eb[NQ×NB], N[NC×NQ], V[NB×NQ], Mpsi[NP×NC]")
+    out.append(src)
+    src, total["jacth"] = emit_function("jacth", ins, [("Dth", J(d, thp, len(thp))), ("Vth", J(vT, thp, len(thp)))],
+                                        "row-major Dth[NQ×(2NQ+NU)], Vth[NB×(2NQ+NU)]  (θ' = q1,q2,u)")
+    out.append(src)
+    out.append("constexpr int OPS_EQ = %d, OPS_JAC = %d, OPS_JACTH = %d;" % (total["eq"], total["jac"], total["jacth"]))
+    out.append("} }  // namespace od::gen_%s" % m["name"])
+    return "\n".join(out) + "\n"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# dense models (rocket dynamics, rocket thrust projection): r, rz (row-major dense), rθ' columns
+# ---------------------------------------------------------------------------------------------------------------------
+def model_rocket():
+    z, th = vec("z", 12), vec("t", 16)
+    x, u, h = th[0:12], th[12:15], th[15]
+    mass, length = 1.0, 1.0
+    Jd = [1.0 / 12.0, 1.0 / 12.0, 1.0e-5]
+    g = [0.0, 0.0, -9.81]
+
+    def f(s):
+        r, v, w = s[3:6], s[6:9], s[9:12]
+        rr = sum(a * a for a in r)
+        wr = sum(a * bb for a, bb in zip(w, r))
+        cx = [w[1] * r[2] - w[2] * r[1], w[2] * r[0] - w[0] * r[2], w[0] * r[1] - w[1] * r[0]]
+        rd = [sp.Rational(1, 4) * ((1 - rr) * w[i] - 2 * cx[i] + 2 * wr * r[i]) for i in range(3)]
+        den = (1 + rr) ** 2
+        rF = [r[1] * u[2] - r[2] * u[1], r[2] * u[0] - r[0] * u[2], r[0] * u[1] - r[1] * u[0]]
+        rrF = [r[1] * rF[2] - r[2] * rF[1], r[2] * rF[0] - r[0] * rF[2], r[0] * rF[1] - r[1] * rF[0]]
+        vd = [g[i] + (1.0 / mass) * (u[i] + 8 * rrF[i] / den + 4 * (1 - rr) * rF[i] / den) for i in range(3)]
+        tau = [length * u[1], -length * u[0], 0]
+        Jw = [Jd[i] * w[i] for i in range(3)]
+        wJw = [w[1] * Jw[2] - w[2] * Jw[1], w[2] * Jw[0] - w[0] * Jw[2], w[0] * Jw[1] - w[1] * Jw[0]]
+        wd = [(1.0 / Jd[i]) * (tau[i] - wJw[i]) for i in range(3)]
+        return list(v) + rd + vd + wd
+
+    xm = [(x[i] + z[i]) / 2 for i in range(12)]
+    fm = f(xm)
+    r = [z[i] - (x[i] + h * fm[i]) for i in range(12)]
+    return dict(name="rocket", NZ=12, NTH=16, NTHP=15, z=z, th=th, r=r, kappa_rows=[])
+
+
+def model_rocket_proj():
+    z, th = vec("z", 10), vec("t", 4)
+    u, p, s, w, y, v = z[0:3], z[3], z[4], z[5], z[6], z[7:10]
+    r = [u[0] - th[0] - v[0], u[1] - th[1] - v[1], u[2] - th[2] - v[2] - (y + p), th[3] - u[2] - s, -y - w,
+         w * s, p * u[2],
+         u[2] * v[2] + u[0] * v[0] + u[1] * v[1], u[2] * v[0] + v[2] * u[0], u[2] * v[1] + v[2] * u[1]]
+    return dict(name="rocket_proj", NZ=10, NTH=4, NTHP=3, z=z, th=th, r=r, kappa_rows=[5, 6, 7])
+
+
+def gen_dense(m):
+    z, th = m["z"], m["th"]
+    r = sp.Matrix(m["r"])
+    ins = [("z", z), ("th", th)]
+    out = ["// GENERATED by tools/codegen/gen_models.py — do not edit.  Model: %s" % m["name"],
+           "// Dense residual r(z;θ,κ=0), Jacobian rz (row-major NZ×NZ) and rθ' (row-major NZ×NTHP).",
+           "#pragma once", "namespace od { namespace gen_%s {" % m["name"],
+           "constexpr int NZ = %d, NTH = %d, NTHP = %d;" % (m["NZ"], m["NTH"], m["NTHP"]), ""]
+    src, o1 = emit_function("res", ins, [("r", r)], "r(z;θ) without the −κ shift of the bilinear rows")
+    out.append(src)
+    src, o2 = emit_function("jac", ins, [("rz", list(r.jacobian(sp.Matrix(z))))], "rz, row-major")
+    out.append(src)
+    src, o3 = emit_function("jacth", ins, [("rth", list(r.jacobian(sp.Matrix(th[:m["NTHP"]]))))], "rθ', row-major")
+    out.append(src)
+    out.append("constexpr int OPS_RES = %d, OPS_JAC = %d, OPS_JACTH = %d;" % (o1, o2, o3))
+    out.append("} }  // namespace od::gen_%s" % m["name"])
+    return "\n".join(out) + "\n"
+
+
+def main():
+    only = set(sys.argv[1:])
+    os.makedirs(OUT, exist_ok=True)
+    contact = [("hopper", model_hopper), ("acrobot_impact", lambda: _acrobot(True)), ("acrobot_nominal", lambda: _acrobot(False)),
+               ("cartpole_friction", lambda: _cartpole(True)), ("cartpole_frictionless", lambda: _cartpole(False)),
+               ("planar_push", model_planar_push)]
+    dense = [("rocket", model_rocket), ("rocket_proj", model_rocket_proj)]
+    for name, fn in contact:
+        if only and name not in only:
+            continue
+        sys.stderr.write("[%s]\n" % name)
+        open(os.path.join(OUT, "model_%s.cuh" % name), "w").write(gen_contact(fn()))
+    for name, fn in dense:
+        if only and name not in only:
+            continue
+        sys.stderr.write("[%s]\n" % name)
+        open(os.path.join(OUT, "model_%s.cuh" % name), "w").write(gen_dense(fn()))
+
+
+if __name__ == "__main__":
+    main()
