@@ -42,46 +42,71 @@ struct SolverOpts {           // RoboDojo InteriorPointOptions as set at referen
 // status nibble: 0 converged, 1 iteration cap, 2 non-finite iterate or singular system
 enum : int { ST_OK = 0, ST_MAXIT = 1, ST_FAIL = 2 };
 
-// CVXOPT §8.2 step to the boundary of the second-order cone for λ − αΔ, λ=(l0; l1..), returns min(1, τ α_max)
+// Step lengths are tracked as fractions num/den (den > 0) and compared by cross-multiplication, so that a whole step-length
+// computation costs one division instead of one per cone variable (fp64 division is ~20 instructions on the GPU).
+OD_HD void frac_min(double& bn, double& bd, double n, double d) { if (n * bd < bn * d) { bn = n; bd = d; } }
+
+// CVXOPT §8.2 step to the boundary of the second-order cone for λ − αΔ, λ=(l0; l1..): candidate α = τ / (‖ρ_v‖ − ρ_s) when that
+// denominator is positive (same formula, including the 1e-25 clamp, as the oracle's soc_step; reciprocals are shared).
 template <int DIM>
-OD_HD double soc_step(double l0, const double* l1, double d0, const double* d1, double tau) {
+OD_HD void soc_step(double l0, const double* l1, double d0, const double* d1, double tau, double& bn, double& bd) {
     double ll = l0 * l0, lD = l0 * (-d0);
 #pragma unroll
     for (int i = 0; i < DIM; ++i) { ll -= l1[i] * l1[i]; lD -= l1[i] * (-d1[i]); }
     ll = fmax(ll, 1e-25);
-    const double sq = sqrt(ll);
-    const double rho_s = lD / ll;
-    const double coef = (lD / sq + (-d0)) / (l0 / sq + 1.0);
+    const double inv_ll = 1.0 / ll;
+    const double inv_sq = sqrt(ll) * inv_ll;
+    const double rho_s = lD * inv_ll;
+    const double coef = (lD * inv_sq + (-d0)) / (l0 * inv_sq + 1.0);
     double nv = 0.0;
+    if (DIM == 1) {
+        nv = fabs(((-d1[0]) - coef * l1[0] * inv_sq) * inv_sq);
+    } else {
 #pragma unroll
-    for (int i = 0; i < DIM; ++i) { const double rv = ((-d1[i]) - coef * l1[i] / sq) / sq; nv += rv * rv; }
-    nv = sqrt(nv);
-    double a = 1.0;
-    if (nv - rho_s > 0.0) a = fmin(a, tau / (nv - rho_s));
-    return a;
+        for (int i = 0; i < DIM; ++i) { const double rv = ((-d1[i]) - coef * l1[i] * inv_sq) * inv_sq; nv += rv * rv; }
+        nv = sqrt(nv);
+    }
+    const double den = nv - rho_s;
+    if (den > 0.0) frac_min(bn, bd, tau, den);
 }
 
 template <int N> struct cmax1 { static constexpr int v = N > 0 ? N : 1; };
 
-template <class M>
+// G lanes cooperate on one problem (G = 1: one thread per problem — the throughput configuration; G = 4/8: the latency
+// configuration for small batches, where 4096 problems would otherwise occupy one warp per SM).  All lanes of a group hold
+// identical replicated state (z, r, direction) and evaluate the model redundantly; only the O(n³) factorisation is split by rows.
+// PPB = problems per block; the per-problem workspace is lane-interleaved in shared memory: element e of problem p at ws[e·PPB + p].
+template <class M, int G = 1, int PPB = 1>
 struct ContactIP {
     static constexpr int NQ = M::NQ, NU = M::NU, NC = M::NC, NP = M::NP, NB = M::NB, NTH = M::NTH;
     static constexpr int NC1 = cmax1<NC>::v, NP1 = cmax1<NP>::v, NB1 = cmax1<NB>::v;
     static constexpr int NTP = 2 * NQ + NU;              // θ' = (q1, q2, u): the sensitivity columns that are returned
     static constexpr int NCONE = NC + NP;                // cone degree (orthant pairs + second-order cones)
+    static constexpr int NR = NQ + NC + NB + NP;         // reduced system size
+    static constexpr int NRP = (NR % 2 == 0) ? NR + 1 : NR;   // odd row pitch: the G row-owners of a step hit disjoint banks
+    static constexpr int OFF_X = NR * NRP;               // NTP right-hand-side / solution vectors of length NR
+    static constexpr int OFF_CP = OFF_X + NTP * NR;      // column permutation of the rank-revealing factorisation (robust IFT only)
+    static constexpr int WS = OFF_CP + (M::ROBUST_IFT ? NR : 0);   // workspace doubles per problem
 
     struct Z { double q[NQ], gam[NC1], s[NC1], psi[NP1], b[NB1], spsi[NP1], sb[NB1]; };
     // residual in block form; bilinear rows are stored at κ = 0 (r(z;κ) only shifts rgam and rc0 by −κ)
     struct R { double d[NQ], rs[NC1], rpsi[NP1], rv[NB1], rgam[NC1], rc0[NP1], rc1[NB1]; };
-    static constexpr int NR = NQ + NC + NB + NP;         // reduced system size
-    static constexpr int WS = NR * NR + 2 * NR;          // workspace doubles per problem: K (NR×NR) | x (NR) | piv (NR)
     struct Lin {
         double N[NC1 * NQ], V[NB1 * NQ], Mpsi[NP1 * NC1];
-        double* ws; int stride;
+        double ipiv[NR];             // reciprocal pivots
+        int piv[NR];                 // row interchanges (LAPACK convention)
+        double* ws;                  // workspace of this problem (already offset by the problem's slot)
+        int g;                       // lane within the group
+        unsigned gmask;              // __syncwarp mask of the group
         bool ok;
-        OD_HD double& K(int i, int j) const { return ws[(size_t)(i * NR + j) * stride]; }
-        OD_HD double& x(int i) const { return ws[(size_t)(NR * NR + i) * stride]; }
-        OD_HD double& piv(int i) const { return ws[(size_t)(NR * NR + NR + i) * stride]; }
+        OD_HD double& K(int i, int j) const { return ws[(i * NRP + j) * PPB]; }
+        OD_HD double& X(int v, int i) const { return ws[(OFF_X + v * NR + i) * PPB]; }
+        OD_HD double& CP(int i) const { return ws[(OFF_CP + i) * PPB]; }
+        OD_HD void sync() const {
+#ifdef __CUDA_ARCH__
+            if (G > 1) __syncwarp(gmask);
+#endif
+        }
     };
     __host__ __device__ static constexpr int cone_of(int j) {   // friction cone that tangential component j belongs to
         int k = 0;
@@ -122,11 +147,20 @@ struct ContactIP {
     //   d_i  : D Δq + Eγ Δγ + Eb Δb                                              = rd
     //   γ_i  : γ_i N_i Δq + s_i Δγ_i                                             = rgam_i − γ_i rs_i
     //   c0_k : (Σ_j b_j V_j) Δq + sψ_k Mψ_k Δγ + Σ_j sb_j Δb_j + ψ_k Δsψ_k        = rc0_k − sψ_k rpsi_k + Σ_j b_j rv_j
+
+    // ---- linearise at z: model blocks → reduced matrix K → LU with partial pivoting (in the workspace) -----------------
+    //   unknowns x = [Δq | Δγ | Δb | Δsψ];  rows:
+    //   d_i  : D Δq + Eγ Δγ + Eb Δb                                              = rd
+    //   γ_i  : γ_i N_i Δq + s_i Δγ_i                                             = rgam_i − γ_i rs_i
+    //   c0_k : (Σ_j b_j V_j) Δq + sψ_k Mψ_k Δγ + Σ_j sb_j Δb_j + ψ_k Δsψ_k        = rc0_k − sψ_k rpsi_k + Σ_j b_j rv_j
     //   c1_j : ψ_k V_j Δq + sb_j Mψ_k Δγ + sψ_k Δb_j + b_j Δsψ_k                  = rc1_j − sb_j rpsi_k + ψ_k rv_j
     OD_HD static void linearize(const Z& z, const double* th, Lin& L) { assemble(z, th, L); factor(L); }
+    // every lane of the group writes the same values (benign); factor() synchronises before reading
     OD_HD static void assemble(const Z& z, const double* th, Lin& L) {
+        static_assert(NTP >= G, "each lane needs a private scratch vector");
         double D[NQ * NQ], Eg[NQ * NC1], Eb[NQ * NB1];
         M::jac(z.q, z.gam, z.b, th, D, Eg, Eb, L.N, L.V, L.Mpsi);
+        L.sync();                                             // no lane may still be reading the previous factorisation
 #pragma unroll
         for (int i = 0; i < NQ; ++i) {
 #pragma unroll
@@ -175,62 +209,111 @@ struct ContactIP {
             for (int kk = 0; kk < NP; ++kk) L.K(row, NQ + NC + NB + kk) = (kk == k) ? z.b[j] : 0.0;
         }
     }
-    // LU, partial (row) pivoting
+
+    // LU with partial (row) pivoting, fully unrolled: every workspace address is base + immediate except the pivot row.
+    // Pivot search is done redundantly by every lane of the group (same result); the row interchange is split by columns and the
+    // trailing update by rows across the G lanes.
     OD_HD static void factor(Lin& L) {
         bool ok = true;
+        L.sync();
+#pragma unroll
         for (int k = 0; k < NR; ++k) {
             int p = k; double best = fabs(L.K(k, k));
+#pragma unroll
             for (int i = k + 1; i < NR; ++i) { const double a = fabs(L.K(i, k)); if (a > best) { best = a; p = i; } }
-            L.piv(k) = (double)p;
+            L.piv[k] = p;
             ok = ok && (best > 0.0) && (best < INFINITY);
-            if (p != k) for (int j = 0; j < NR; ++j) { const double t = L.K(k, j); L.K(k, j) = L.K(p, j); L.K(p, j) = t; }
-            const double inv = 1.0 / L.K(k, k);
-            L.K(k, k) = inv;                       // keep the reciprocal pivot
-            for (int i = k + 1; i < NR; ++i) {
-                const double l = L.K(i, k) * inv;
-                L.K(i, k) = l;
-                for (int j = k + 1; j < NR; ++j) L.K(i, j) -= l * L.K(k, j);
+            if (G > 1) L.sync();                              // all lanes have read column k before rows move
+            if (p != k) {
+                double* rk = &L.K(k, 0); double* rp = &L.K(p, 0);
+#pragma unroll
+                for (int t = 0; t < (NR + G - 1) / G; ++t) {
+                    const int j = L.g + G * t;
+                    if (G == 1 || j < NR) { const double a = rk[j * PPB]; rk[j * PPB] = rp[j * PPB]; rp[j * PPB] = a; }
+                }
             }
+            if (G > 1) L.sync();
+            const double inv = 1.0 / L.K(k, k);
+            L.ipiv[k] = inv;
+            double prow[NR];
+#pragma unroll
+            for (int j = k + 1; j < NR; ++j) prow[j] = L.K(k, j);
+#pragma unroll
+            for (int t = 0; t < (NR - k - 1 + G - 1) / G; ++t) {
+                const int i = k + 1 + L.g + G * t;
+                if (G == 1 || i < NR) {
+                    double* ri = &L.K(i, 0);
+                    const double l = ri[k * PPB] * inv;
+                    ri[k * PPB] = l;
+#pragma unroll
+                    for (int j = k + 1; j < NR; ++j) ri[j * PPB] -= l * prow[j];
+                }
+            }
+            if (G > 1) L.sync();
         }
         L.ok = ok;
     }
 
-    // x (in the workspace) ← K⁻¹ x
-    OD_HD static void lu_solve(const Lin& L) {
-        for (int k = 0; k < NR; ++k) { const int p = (int)L.piv(k); if (p != k) { const double t = L.x(k); L.x(k) = L.x(p); L.x(p) = t; } }
-        for (int i = 1; i < NR; ++i) { double sacc = L.x(i); for (int j = 0; j < i; ++j) sacc -= L.K(i, j) * L.x(j); L.x(i) = sacc; }
-        for (int i = NR - 1; i >= 0; --i) { double sacc = L.x(i); for (int j = i + 1; j < NR; ++j) sacc -= L.K(i, j) * L.x(j); L.x(i) = sacc * L.K(i, i); }
+    // x ← K⁻¹ x for one right-hand side held in registers; run redundantly by every lane that needs the result.
+    // `scratch` is a workspace vector private to the calling lane (used only for the dynamic-index row interchanges).
+    OD_HD static void lu_solve(const Lin& L, double* x, double* scratch) {
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < NR; ++k) any = any || (L.piv[k] != k);
+        if (any) {                                            // interchanges need run-time indexing: do them in the workspace
+#pragma unroll
+            for (int i = 0; i < NR; ++i) scratch[i * PPB] = x[i];
+#pragma unroll
+            for (int k = 0; k < NR; ++k) {
+                const int p = L.piv[k];
+                if (p != k) { const double t = scratch[k * PPB]; scratch[k * PPB] = scratch[p * PPB]; scratch[p * PPB] = t; }
+            }
+#pragma unroll
+            for (int i = 0; i < NR; ++i) x[i] = scratch[i * PPB];
+        }
+#pragma unroll
+        for (int i = 1; i < NR; ++i) {
+#pragma unroll
+            for (int j = 0; j < i; ++j) x[i] -= L.K(i, j) * x[j];
+        }
+#pragma unroll
+        for (int i = NR - 1; i >= 0; --i) {
+#pragma unroll
+            for (int j = i + 1; j < NR; ++j) x[i] -= L.K(i, j) * x[j];
+            x[i] *= L.ipiv[i];
+        }
     }
 
-    // reduced right-hand side of r into the workspace
-    OD_HD static void load_rhs(const Lin& L, const Z& z, const R& r) {
+    // reduced right-hand side of r
+    OD_HD static void load_rhs(const Z& z, const R& r, double* x) {
 #pragma unroll
-        for (int i = 0; i < NQ; ++i) L.x(i) = r.d[i];
+        for (int i = 0; i < NQ; ++i) x[i] = r.d[i];
 #pragma unroll
-        for (int i = 0; i < NC; ++i) L.x(NQ + i) = r.rgam[i] - z.gam[i] * r.rs[i];
+        for (int i = 0; i < NC; ++i) x[NQ + i] = r.rgam[i] - z.gam[i] * r.rs[i];
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
             double a = r.rc0[k] - z.spsi[k] * r.rpsi[k];
 #pragma unroll
             for (int e = 0; e < M::cone_dim(k); ++e) a += z.b[M::cone_off(k) + e] * r.rv[M::cone_off(k) + e];
-            L.x(NQ + NC + k) = a;
+            x[NQ + NC + k] = a;
         }
 #pragma unroll
-        for (int j = 0; j < NB; ++j) L.x(NQ + NC + NP + j) = r.rc1[j] - z.sb[j] * r.rpsi[cone_of(j)] + z.psi[cone_of(j)] * r.rv[j];
+        for (int j = 0; j < NB; ++j) x[NQ + NC + NP + j] = r.rc1[j] - z.sb[j] * r.rpsi[cone_of(j)] + z.psi[cone_of(j)] * r.rv[j];
     }
 
-    // full Newton direction for right-hand side r:  rz Δ = r
+    // full Newton direction for right-hand side r:  rz Δ = r   (every lane computes the same D)
     OD_HD static void solve(const Lin& L, const Z& z, const R& r, Z& D) {
-        load_rhs(L, z, r);
-        lu_solve(L);
+        double x[NR];
+        load_rhs(z, r, x);
+        lu_solve(L, x, &L.X(L.g, 0));
 #pragma unroll
-        for (int i = 0; i < NQ; ++i) D.q[i] = L.x(i);
+        for (int i = 0; i < NQ; ++i) D.q[i] = x[i];
 #pragma unroll
-        for (int i = 0; i < NC; ++i) D.gam[i] = L.x(NQ + i);
+        for (int i = 0; i < NC; ++i) D.gam[i] = x[NQ + i];
 #pragma unroll
-        for (int j = 0; j < NB; ++j) D.b[j] = L.x(NQ + NC + j);
+        for (int j = 0; j < NB; ++j) D.b[j] = x[NQ + NC + j];
 #pragma unroll
-        for (int k = 0; k < NP; ++k) D.spsi[k] = L.x(NQ + NC + NB + k);
+        for (int k = 0; k < NP; ++k) D.spsi[k] = x[NQ + NC + NB + k];
         // substituted variables
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
@@ -256,24 +339,25 @@ struct ContactIP {
     }
 
     // ---- cone utilities --------------------------------------------------------------------------------------------
+    // ---- cone utilities --------------------------------------------------------------------------------------------
     OD_HD static double step_length(const Z& z, const Z& D, double tau) {
-        double a = 1.0;
+        double bn = 1.0, bd = 1.0;                            // α = min(1, candidates)
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
-            if (D.gam[i] > 0.0) a = fmin(a, tau * z.gam[i] / D.gam[i]);
-            if (D.s[i] > 0.0) a = fmin(a, tau * z.s[i] / D.s[i]);
+            if (D.gam[i] > 0.0) frac_min(bn, bd, tau * z.gam[i], D.gam[i]);
+            if (D.s[i] > 0.0) frac_min(bn, bd, tau * z.s[i], D.s[i]);
         }
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
             if (M::cone_dim(k) == 1) {
-                a = fmin(a, soc_step<1>(z.psi[k], &z.b[M::cone_off(k)], D.psi[k], &D.b[M::cone_off(k)], tau));
-                a = fmin(a, soc_step<1>(z.spsi[k], &z.sb[M::cone_off(k)], D.spsi[k], &D.sb[M::cone_off(k)], tau));
+                soc_step<1>(z.psi[k], &z.b[M::cone_off(k)], D.psi[k], &D.b[M::cone_off(k)], tau, bn, bd);
+                soc_step<1>(z.spsi[k], &z.sb[M::cone_off(k)], D.spsi[k], &D.sb[M::cone_off(k)], tau, bn, bd);
             } else {
-                a = fmin(a, soc_step<2>(z.psi[k], &z.b[M::cone_off(k)], D.psi[k], &D.b[M::cone_off(k)], tau));
-                a = fmin(a, soc_step<2>(z.spsi[k], &z.sb[M::cone_off(k)], D.spsi[k], &D.sb[M::cone_off(k)], tau));
+                soc_step<2>(z.psi[k], &z.b[M::cone_off(k)], D.psi[k], &D.b[M::cone_off(k)], tau, bn, bd);
+                soc_step<2>(z.spsi[k], &z.sb[M::cone_off(k)], D.spsi[k], &D.sb[M::cone_off(k)], tau, bn, bd);
             }
         }
-        return a;
+        return bn / bd;
     }
 
     // Σ ⟨primal − aΔp, dual − aΔd⟩ over all cones
@@ -299,17 +383,16 @@ struct ContactIP {
         for (int j = 0; j < NB; ++j) { c.b[j] = z.b[j] - a * D.b[j]; c.sb[j] = z.sb[j] - a * D.sb[j]; }
     }
 
-    // ---- one predictor–corrector iteration with residual line search (z, r, r_vio, k_vio updated in place) ------------
-    OD_HD static void iterate(const Lin& L, const double* th, const SolverOpts& o, Z& z, R& r, double& r_vio, double& k_vio) {
-        Z D;
-        double kappa = 0.0;
+
+    // Newton direction at z (predictor, centering, Mehrotra corrector) and the step length along it
+    OD_HD static void direction(const Lin& L, const Z& z, const R& r, double r_vio, double k_vio, Z& D, double& alpha) {
         if (NCONE > 0) {
             solve(L, z, r, D);                                   // affine direction
             const double a_aff = step_length(z, D, 1.0);
             const double mu = cone_dot(z, D, 0.0) * (1.0 / (NCONE > 0 ? NCONE : 1));
             const double mu_aff = cone_dot(z, D, a_aff) * (1.0 / (NCONE > 0 ? NCONE : 1));
             const double ratio = fmin(fmax(mu_aff / mu, 0.0), 1.0);
-            kappa = ratio * ratio * ratio * mu;                   // max(σμ, κ_tol/undercut) with undercut = Inf
+            const double kappa = ratio * ratio * ratio * mu;      // max(σμ, κ_tol/undercut) with undercut = Inf
             // corrector right-hand side: r(z;κ) + Δaff_primal ∘ Δaff_dual on the bilinear rows
             R rc = r;
 #pragma unroll
@@ -326,47 +409,122 @@ struct ContactIP {
                 rc.rc0[k] = (r.rc0[k] - kappa) + acc;
             }
             solve(L, z, rc, D);
+            const double viol = fmax(r_vio, k_vio);
+            alpha = step_length(z, D, fmax(0.95, 1.0 - viol * viol));
         } else {
-            solve(L, z, r, D);                                   // no cones: plain Newton direction
+            solve(L, z, r, D);                                   // no cones: plain Newton direction, full step
+            alpha = 1.0;
         }
-        const double viol = fmax(r_vio, k_vio);
-        const double tau = fmax(0.95, 1.0 - viol * viol);
-        double alpha = (NCONE > 0) ? step_length(z, D, tau) : 1.0;
-        Z zc; R rc2; double rv2, kv2;
-        candidate(z, D, alpha, zc);
-        for (int ls = 1; ls <= o.max_ls; ++ls) {
-            residual(zc, th, rc2, rv2, kv2);
-            if (rv2 <= r_vio || kv2 <= k_vio) break;
-            alpha *= o.ls_scale;
-            candidate(z, D, alpha, zc);
-            if (ls == o.max_ls) residual(zc, th, rc2, rv2, kv2);
-        }
-        z = zc; r = rc2; r_vio = rv2; k_vio = kv2;
     }
 
     // ---- IFT: ∂q3/∂θ' = −(rz⁻¹ rθ')[q rows]; column c of the NQ×NTP column-major result goes to dq1 / dq2 / du ---------
+    // The NTP reduced right-hand sides are written to the workspace (redundantly by all lanes), then lane g solves columns
+    // g, g+G, … with the factorisation of rz at the final iterate.
     OD_HD static void sensitivities(const Lin& L, const Z& z, const double* th, double* dq1, double* dq2, double* du) {
-        double Dth[NQ * NTP], Vth[NB1 * NTP];
-        M::jacth(z.q, z.gam, z.b, th, Dth, Vth);
-        R r;
+        {
+            double Dth[NQ * NTP], Vth[NB1 * NTP];
+            M::jacth(z.q, z.gam, z.b, th, Dth, Vth);
+            R r;
 #pragma unroll
-        for (int i = 0; i < NC1; ++i) { r.rs[i] = 0.0; r.rgam[i] = 0.0; }
+            for (int i = 0; i < NC1; ++i) { r.rs[i] = 0.0; r.rgam[i] = 0.0; }
 #pragma unroll
-        for (int i = 0; i < NP1; ++i) { r.rpsi[i] = 0.0; r.rc0[i] = 0.0; }
+            for (int i = 0; i < NP1; ++i) { r.rpsi[i] = 0.0; r.rc0[i] = 0.0; }
 #pragma unroll
-        for (int i = 0; i < NB1; ++i) r.rc1[i] = 0.0;
+            for (int i = 0; i < NB1; ++i) r.rc1[i] = 0.0;
 #pragma unroll
-        for (int c = 0; c < NTP; ++c) {
+            for (int c = 0; c < NTP; ++c) {
 #pragma unroll
-            for (int i = 0; i < NQ; ++i) r.d[i] = Dth[i * NTP + c];
+                for (int i = 0; i < NQ; ++i) r.d[i] = Dth[i * NTP + c];
 #pragma unroll
-            for (int j = 0; j < NB; ++j) r.rv[j] = Vth[j * NTP + c];
-            load_rhs(L, z, r);
-            lu_solve(L);
+                for (int j = 0; j < NB; ++j) r.rv[j] = Vth[j * NTP + c];
+                double x[NR];
+                load_rhs(z, r, x);
+#pragma unroll
+                for (int i = 0; i < NR; ++i) L.X(c, i) = x[i];
+            }
+        }
+        L.sync();
+#pragma unroll 1
+        for (int c = L.g; c < NTP; c += G) {
+            double* col = &L.X(c, 0);
+            double x[NR];
+#pragma unroll
+            for (int i = 0; i < NR; ++i) x[i] = col[i * PPB];
+            lu_solve(L, x, col);
             double* dst = (c < NQ) ? (dq1 + c * NQ) : (c < 2 * NQ) ? (dq2 + (c - NQ) * NQ) : (du + (c - 2 * NQ) * NQ);
 #pragma unroll
-            for (int i = 0; i < NQ; ++i) dst[i] = -L.x(i);
+            for (int i = 0; i < NQ; ++i) dst[i] = -x[i];
         }
+        L.sync();
+    }
+
+    // ---- robust IFT for models with redundant contact constraints (planar push: 4 corner contacts on a 3-DoF block) ---------
+    // At a sticking iterate with κ → 0 the friction multipliers are not unique and rz is numerically rank deficient, while the
+    // q rows of δz stay well defined.  Partial pivoting then divides by rounding-level pivots (or hits an exact zero); here the
+    // factorisation at the final iterate uses COMPLETE pivoting, stops at the numerical rank, and solves the consistent system
+    // with the free multipliers set to zero.  Runs once per problem, on lane 0 of the group (dynamic loops: small code).
+    OD_HD static bool sensitivities_robust(Lin& L, const Z& z, const double* th, double* dq1, double* dq2, double* du) {
+        {
+            double Dth[NQ * NTP], Vth[NB1 * NTP];
+            M::jacth(z.q, z.gam, z.b, th, Dth, Vth);
+            R r;
+#pragma unroll
+            for (int i = 0; i < NC1; ++i) { r.rs[i] = 0.0; r.rgam[i] = 0.0; }
+#pragma unroll
+            for (int i = 0; i < NP1; ++i) { r.rpsi[i] = 0.0; r.rc0[i] = 0.0; }
+#pragma unroll
+            for (int i = 0; i < NB1; ++i) r.rc1[i] = 0.0;
+#pragma unroll
+            for (int c = 0; c < NTP; ++c) {
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) r.d[i] = Dth[i * NTP + c];
+#pragma unroll
+                for (int j = 0; j < NB; ++j) r.rv[j] = Vth[j * NTP + c];
+                double x[NR];
+                load_rhs(z, r, x);
+#pragma unroll
+                for (int i = 0; i < NR; ++i) L.X(c, i) = x[i];
+            }
+        }
+        L.sync();
+        int rank = NR;
+        if (L.g == 0) {
+            double amax = 0.0;
+            for (int i = 0; i < NR; ++i) for (int j = 0; j < NR; ++j) amax = fmax(amax, fabs(L.K(i, j)));
+            const double tol = 1e-11 * amax;
+            for (int k = 0; k < NR; ++k) {
+                int p = k, q = k; double best = -1.0;
+                for (int i = k; i < NR; ++i) for (int j = k; j < NR; ++j) { const double a = fabs(L.K(i, j)); if (a > best) { best = a; p = i; q = j; } }
+                if (!(best > tol)) { rank = k; break; }
+                L.CP(k) = (double)q;
+                if (p != k) {
+                    for (int j = 0; j < NR; ++j) { const double t = L.K(k, j); L.K(k, j) = L.K(p, j); L.K(p, j) = t; }
+                    for (int c = 0; c < NTP; ++c) { const double t = L.X(c, k); L.X(c, k) = L.X(c, p); L.X(c, p) = t; }     // row swap applied to every rhs
+                }
+                if (q != k) for (int i = 0; i < NR; ++i) { const double t = L.K(i, k); L.K(i, k) = L.K(i, q); L.K(i, q) = t; }
+                const double inv = 1.0 / L.K(k, k);
+                for (int i = k + 1; i < NR; ++i) {
+                    const double l = L.K(i, k) * inv;
+                    if (l != 0.0) {
+                        for (int j = k + 1; j < NR; ++j) L.K(i, j) -= l * L.K(k, j);
+                        for (int c = 0; c < NTP; ++c) L.X(c, i) -= l * L.X(c, k);                                        // forward elimination of every rhs
+                    }
+                }
+            }
+            for (int c = 0; c < NTP; ++c) {
+                for (int i = rank; i < NR; ++i) L.X(c, i) = 0.0;                                  // free (non-unique) unknowns
+                for (int i = rank - 1; i >= 0; --i) {
+                    double sacc = L.X(c, i);
+                    for (int j = i + 1; j < rank; ++j) sacc -= L.K(i, j) * L.X(c, j);
+                    L.X(c, i) = sacc / L.K(i, i);
+                }
+                for (int k = rank - 1; k >= 0; --k) { const int q = (int)L.CP(k); if (q != k) { const double t = L.X(c, k); L.X(c, k) = L.X(c, q); L.X(c, q) = t; } }
+                double* dst = (c < NQ) ? (dq1 + c * NQ) : (c < 2 * NQ) ? (dq2 + (c - NQ) * NQ) : (du + (c - 2 * NQ) * NQ);
+                for (int i = 0; i < NQ; ++i) dst[i] = -L.X(c, i);
+            }
+        }
+        L.sync();
+        return rank > 0;
     }
 
     // initialize_z! (reference src/models/planar_push/simulator.jl:52-60 and the same pattern in the other models)
@@ -413,15 +571,17 @@ struct StepArgs {
     SolverOpts opts;
 };
 
-// One thread = one problem.  A single iterate sequence serves both simulators of ImplicitDynamics: eval_sim and grad_sim
+// One problem (G cooperating lanes).  A single iterate sequence serves both simulators of ImplicitDynamics: eval_sim and grad_sim
 // (reference src/dynamics.jl:60-64) start from the same initialisation and differ only in κ_tol, so the looser one is a prefix
 // of the tighter one.  The IFT is taken at the first iterate meeting the gradient tolerance, q3 at the first meeting the eval one.
-template <class M>
-OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const int ws_stride) {
-    typedef ContactIP<M> IP;
+// The loop is a small state machine with ONE call site each for the residual, the factorisation and the direction, so that the
+// instruction footprint stays small and lanes of a warp that are in different phases (line search / new iteration) share code.
+template <class M, int G, int PPB>
+OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const int g, const unsigned gmask) {
+    typedef ContactIP<M, G, PPB> IP;
     constexpr int NQ = M::NQ, NU = M::NU;
     double th[M::NTH];
-    typename IP::Z z;
+    typename IP::Z z, D, zc;
     {
         const int src = a.eta ? i / (a.n_eta + 1) : i;
         const int pert = a.eta ? i % (a.n_eta + 1) : 0;
@@ -446,12 +606,26 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
         th[M::NTH - 1] = a.h;
         IP::init_z(q2v, z);
     }
+    typename IP::Lin L;
+    L.ws = ws; L.g = g; L.gmask = gmask; L.ok = true;
     typename IP::R r;
-    double r_vio, k_vio;
-    IP::residual(z, th, r, r_vio, k_vio);
-    bool eval_done = !a.want_eval, grad_done = !a.want_grad;
-    int it = 0, it_e = 0, it_g = 0, st_e = 0, st_g = 0;
+    double r_vio = 0.0, k_vio = 0.0, alpha = 0.0;
+    D = z;                                  // any finite values: the first candidate uses alpha = 0
+    bool first = true, eval_done = !a.want_eval, grad_done = !a.want_grad;
+    int it = 0, ls = 0, it_e = 0, it_g = 0, st_e = 0, st_g = 0;
     for (;;) {
+        // ---- candidate z − αΔ and its residual (the only residual call site) ----------------------------------------------
+        typename IP::R rc; double rv2, kv2;
+        IP::candidate(z, D, alpha, zc);
+        IP::residual(zc, th, rc, rv2, kv2);
+        if (!(first || rv2 <= r_vio || kv2 <= k_vio || ls >= a.opts.max_ls)) {   // residual line search: halve and retry
+            alpha *= a.opts.ls_scale; ++ls;
+            continue;
+        }
+        z = zc; r = rc; r_vio = rv2; k_vio = kv2;
+        if (!first) ++it;
+        first = false;
+        // ---- accepted iterate: termination tests ----------------------------------------------------------------------------
         const bool bad = !IP::finite(z, r_vio, k_vio);
         const bool capped = it >= a.opts.max_iter;
         const bool rok = r_vio < a.opts.r_tol;
@@ -459,7 +633,7 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
         const bool conv_g = rok && (k_vio < a.opts.kappa_grad_tol);
         if (!eval_done && (conv_e || capped || bad)) {
             eval_done = true; it_e = it; st_e = bad ? ST_FAIL : (conv_e ? ST_OK : ST_MAXIT);
-            if (a.q3) {
+            if (a.q3 && g == 0) {
                 double* o = a.q3 + (size_t)i * a.out_stride_q3;
 #pragma unroll
                 for (int k = 0; k < NQ; ++k) o[k] = z.q[k];
@@ -468,33 +642,37 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
         const bool need_ift = !grad_done && (conv_g || capped || bad);
         const bool do_iter = !bad && !capped && (!eval_done || (!grad_done && !need_ift));
         if (!need_ift && !do_iter) break;
-        typename IP::Lin L;
-        L.ws = ws; L.stride = ws_stride;
-        IP::linearize(z, th, L);
-        if (need_ift) {
+        if (M::ROBUST_IFT && need_ift) {
+            IP::assemble(z, th, L);
+            bool okr = true;
+            if (a.dq1) okr = IP::sensitivities_robust(L, z, th, a.dq1 + (size_t)i * a.out_stride_dq, a.dq2 + (size_t)i * a.out_stride_dq, a.du + (size_t)i * a.out_stride_du);
+            grad_done = true; it_g = it; st_g = (bad || !okr) ? ST_FAIL : (conv_g ? ST_OK : ST_MAXIT);
+        }
+        if (do_iter || (need_ift && !M::ROBUST_IFT)) IP::linearize(z, th, L);
+        if (need_ift && !M::ROBUST_IFT) {
             grad_done = true; it_g = it; st_g = (bad || !L.ok) ? ST_FAIL : (conv_g ? ST_OK : ST_MAXIT);
-            if (a.dq1) {
-                IP::sensitivities(L, z, th, a.dq1 + (size_t)i * a.out_stride_dq, a.dq2 + (size_t)i * a.out_stride_dq, a.du + (size_t)i * a.out_stride_du);
-            }
+            if (a.dq1) IP::sensitivities(L, z, th, a.dq1 + (size_t)i * a.out_stride_dq, a.dq2 + (size_t)i * a.out_stride_dq, a.du + (size_t)i * a.out_stride_du);
         }
-        if (do_iter) {
-            if (!L.ok) { st_e = eval_done ? st_e : ST_FAIL; st_g = grad_done ? st_g : ST_FAIL; it_e = eval_done ? it_e : it; it_g = grad_done ? it_g : it; break; }
-            IP::iterate(L, th, a.opts, z, r, r_vio, k_vio);
-            ++it;
-        } else {
-            break;
-        }
+        if (!do_iter) break;
+        if (!L.ok) { if (!eval_done) { st_e = ST_FAIL; it_e = it; } if (!grad_done) { st_g = ST_FAIL; it_g = it; } break; }
+        IP::direction(L, z, r, r_vio, k_vio, D, alpha);
+        ls = 0;
     }
-    if (a.status) a.status[i] = st_e | (st_g << 4);
-    if (a.iters) a.iters[i] = it_e | (it_g << 16);
+    if (g == 0) {
+        if (a.status) a.status[i] = st_e | (st_g << 4);
+        if (a.iters) a.iters[i] = it_e | (it_g << 16);
+    }
 }
 
-template <class M, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) contact_step_kernel(const StepArgs a) {
-    extern __shared__ double od_smem[];            // BLOCK × ContactIP<M>::WS doubles, lane-interleaved
-    const int i = blockIdx.x * BLOCK + threadIdx.x;
+// BLOCK = G·PPB threads; dynamic shared memory = PPB × ContactIP::WS doubles.
+template <class M, int G, int PPB>
+__global__ void __launch_bounds__(G * PPB) contact_step_kernel(const StepArgs a) {
+    extern __shared__ double od_smem[];
+    const int slot = threadIdx.x / G, g = threadIdx.x % G;
+    const int i = blockIdx.x * PPB + slot;
     if (i >= a.B) return;
-    contact_step_one<M>(a, i, od_smem + threadIdx.x, BLOCK);
+    const unsigned gmask = (G >= 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) - g));
+    contact_step_one<M, G, PPB>(a, i, od_smem + slot, g, gmask);
 }
 
 }  // namespace od

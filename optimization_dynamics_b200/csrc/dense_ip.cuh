@@ -46,20 +46,20 @@ struct DenseIP {
     }
 
     OD_HD static double step_length(const double* z, const double* D, double tau) {
-        double a = 1.0;
+        double bn = 1.0, bd = 1.0;
         for (int k = 0; k < M::NORT; ++k) {
             const int ip = M::ort_p(k), id = M::ort_d(k);
-            if (D[ip] > 0.0) a = fmin(a, tau * z[ip] / D[ip]);
-            if (D[id] > 0.0) a = fmin(a, tau * z[id] / D[id]);
+            if (D[ip] > 0.0) frac_min(bn, bd, tau * z[ip], D[ip]);
+            if (D[id] > 0.0) frac_min(bn, bd, tau * z[id], D[id]);
         }
         for (int c = 0; c < M::NSOC; ++c) {
             double l1[2], d1[2];
             l1[0] = z[M::soc_p(c, 1)]; l1[1] = z[M::soc_p(c, 2)]; d1[0] = D[M::soc_p(c, 1)]; d1[1] = D[M::soc_p(c, 2)];
-            a = fmin(a, soc_step<2>(z[M::soc_p(c, 0)], l1, D[M::soc_p(c, 0)], d1, tau));
+            soc_step<2>(z[M::soc_p(c, 0)], l1, D[M::soc_p(c, 0)], d1, tau, bn, bd);
             l1[0] = z[M::soc_d(c, 1)]; l1[1] = z[M::soc_d(c, 2)]; d1[0] = D[M::soc_d(c, 1)]; d1[1] = D[M::soc_d(c, 2)];
-            a = fmin(a, soc_step<2>(z[M::soc_d(c, 0)], l1, D[M::soc_d(c, 0)], d1, tau));
+            soc_step<2>(z[M::soc_d(c, 0)], l1, D[M::soc_d(c, 0)], d1, tau, bn, bd);
         }
-        return a;
+        return bn / bd;
     }
     OD_HD static double cone_dot(const double* z, const double* D, double a) {
         double s = 0.0;

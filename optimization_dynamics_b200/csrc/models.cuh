@@ -15,9 +15,10 @@
 
 namespace od {
 
-#define OD_CONTACT_MODEL(NAME, NS, NFRIC, OFF_EXPR, DIM_EXPR)                                                                     \
+#define OD_CONTACT_MODEL(NAME, NS, NFRIC, OFF_EXPR, DIM_EXPR, ROBUST)                                                                     \
     struct NAME {                                                                                                                \
         static constexpr int NQ = NS::NQ, NU = NS::NU, NC = NS::NC, NP = NS::NP, NB = NS::NB, NTH = NS::NTH, NF = NFRIC;           \
+        static constexpr bool ROBUST_IFT = ROBUST;   /* redundant contact constraints: rank-revealing IFT (contact_ip.cuh) */  \
         OD_HD static constexpr int cone_off(int k) { return OFF_EXPR; }                                             \
         OD_HD static constexpr int cone_dim(int k) { return DIM_EXPR; }                                             \
         OD_HD static void eq(const double* q, const double* g, const double* b, const double* th, double* d,  \
@@ -30,12 +31,12 @@ namespace od {
     };
 
 // cone k of the friction block: offset into b / sb and number of tangential components
-OD_CONTACT_MODEL(HopperModel, gen_hopper, 2, k, 1)
-OD_CONTACT_MODEL(AcrobotImpactModel, gen_acrobot_impact, 0, 0, 0)
-OD_CONTACT_MODEL(AcrobotNominalModel, gen_acrobot_nominal, 0, 0, 0)
-OD_CONTACT_MODEL(CartpoleFrictionModel, gen_cartpole_friction, 2, k, 1)
-OD_CONTACT_MODEL(CartpoleFrictionlessModel, gen_cartpole_frictionless, 0, 0, 0)
-OD_CONTACT_MODEL(PlanarPushModel, gen_planar_push, 0, 2 * k, (k < 4 ? 2 : 1))
+OD_CONTACT_MODEL(HopperModel, gen_hopper, 2, k, 1, false)
+OD_CONTACT_MODEL(AcrobotImpactModel, gen_acrobot_impact, 0, 0, 0, false)
+OD_CONTACT_MODEL(AcrobotNominalModel, gen_acrobot_nominal, 0, 0, 0, false)
+OD_CONTACT_MODEL(CartpoleFrictionModel, gen_cartpole_friction, 2, k, 1, false)
+OD_CONTACT_MODEL(CartpoleFrictionlessModel, gen_cartpole_frictionless, 0, 0, 0, false)
+OD_CONTACT_MODEL(PlanarPushModel, gen_planar_push, 0, 2 * k, (k < 4 ? 2 : 1), true)
 #undef OD_CONTACT_MODEL
 
 struct RocketDynModel {

@@ -8,7 +8,7 @@
 
 using namespace od;
 
-template <class M> static void run_contact(const StepArgs& a) { double ws[ContactIP<M>::WS]; for (int i = 0; i < a.B; ++i) contact_step_one<M>(a, i, ws, 1); }
+template <class M> static void run_contact(const StepArgs& a) { double ws[ContactIP<M>::WS]; for (int i = 0; i < a.B; ++i) contact_step_one<M, 1, 1>(a, i, ws, 0, 0u); }
 
 extern "C" int hc_contact_step(int model, int B, const double* q1, const double* q2, const double* u, int nq, int nu, double h, const double* fric,
                                double r_tol, double k_eval, double k_grad, int max_iter, int max_ls, int want_eval, int want_grad,
@@ -64,7 +64,7 @@ template <class M> static void resid_t(const double* zz, const double* th, doubl
     for (int i = 0; i < M::NP; ++i) *o++ = r.rc0[i];
     for (int i = 0; i < M::NB; ++i) *o++ = r.rc1[i];
     typename IP::Lin L; typename IP::Z D; double ws[IP::WS];
-    L.ws = ws; L.stride = 1;
+    L.ws = ws; L.g = 0; L.gmask = 0u;
     IP::linearize(z, th, L);
     IP::solve(L, z, r, D);
     o = dir;
@@ -102,7 +102,7 @@ template <class M> static void sens_t(const double* zz, const double* th, double
     for (int i = 0; i < M::NP; ++i) z.spsi[i] = *p++;
     for (int i = 0; i < M::NB; ++i) z.sb[i] = *p++;
     typename IP::Lin L; double ws[IP::WS];
-    L.ws = ws; L.stride = 1;
+    L.ws = ws; L.g = 0; L.gmask = 0u;
     IP::linearize(z, th, L);
     IP::sensitivities(L, z, th, dq1, dq2, du);
 }
@@ -129,9 +129,9 @@ template <class M> static void K_t(const double* zz, const double* th, double* K
     for (int i = 0; i < M::NP; ++i) z.spsi[i] = *p++;
     for (int i = 0; i < M::NB; ++i) z.sb[i] = *p++;
     typename IP::Lin L; double ws[IP::WS];
-    L.ws = ws; L.stride = 1;
+    L.ws = ws; L.g = 0; L.gmask = 0u;
     IP::assemble(z, th, L);
-    for (int i = 0; i < IP::NR * IP::NR; ++i) Kout[i] = ws[i];
+    for (int i = 0; i < IP::NR; ++i) for (int j = 0; j < IP::NR; ++j) Kout[i * IP::NR + j] = L.K(i, j);
 }
 extern "C" int hc_contact_K(int model, const double* z, const double* th, double* K) {
     switch (model) {

@@ -25,7 +25,7 @@ def test_solver_templates_match_oracle(name):
     r = H.step(name, q1, q2, u, h, ke, kg, fric=fric)
     tr = lambda a: a.transpose(0, 2, 1)
     eq, eg = compare(name, e, g, r["q3"], tr(r["dq1"]), tr(r["dq2"]), tr(r["du"]), r["st_eval"], r["st_grad"],
-                     grad_outlier_fraction=0.01 if name == "planar_push" else 0.0)
+                     grad_outlier_fraction=0.0)
     # same iterate sequence ⇒ same iteration counts on every comparable sample
     ok = (e["status"] == 0) & (r["st_eval"] == 0) & (e["margin"] > 1e-6)
     assert (e["iters"][ok] != r["it_eval"][ok]).mean() <= 0.002
