@@ -84,8 +84,9 @@ struct ContactIP {
     static constexpr int NCONE = NC + NP;                // cone degree (orthant pairs + second-order cones)
     static constexpr int NR = NQ + NC + NB + NP;         // reduced system size
     static constexpr int NRP = (NR % 2 == 0) ? NR + 1 : NR;   // odd row pitch: the G row-owners of a step hit disjoint banks
-    static constexpr int OFF_X = NR * NRP;               // NTP right-hand-side / solution vectors of length NR
-    static constexpr int OFF_CP = OFF_X + NTP * NR;      // column permutation of the rank-revealing factorisation (robust IFT only)
+    static constexpr int OFF_X = NR * NRP;               // NTP right-hand-side / solution vectors, pitch NRP (odd: lane-private vectors on disjoint banks)
+    static constexpr int OFF_PIV = OFF_X + NTP * NRP;    // row interchanges of the LU (LAPACK convention), stored as doubles
+    static constexpr int OFF_CP = OFF_PIV + NR;          // column permutation of the rank-revealing factorisation (robust IFT only)
     static constexpr int WS = OFF_CP + (M::ROBUST_IFT ? NR : 0);   // workspace doubles per problem
 
     struct Z { double q[NQ], gam[NC1], s[NC1], psi[NP1], b[NB1], spsi[NP1], sb[NB1]; };
@@ -93,14 +94,13 @@ struct ContactIP {
     struct R { double d[NQ], rs[NC1], rpsi[NP1], rv[NB1], rgam[NC1], rc0[NP1], rc1[NB1]; };
     struct Lin {
         double N[NC1 * NQ], V[NB1 * NQ], Mpsi[NP1 * NC1];
-        double ipiv[NR];             // reciprocal pivots
-        int piv[NR];                 // row interchanges (LAPACK convention)
         double* ws;                  // workspace of this problem (already offset by the problem's slot)
         int g;                       // lane within the group
         unsigned gmask;              // __syncwarp mask of the group
         bool ok;
         OD_HD double& K(int i, int j) const { return ws[(i * NRP + j) * PPB]; }
-        OD_HD double& X(int v, int i) const { return ws[(OFF_X + v * NR + i) * PPB]; }
+        OD_HD double& X(int v, int i) const { return ws[(OFF_X + v * NRP + i) * PPB]; }
+        OD_HD double& PIV(int i) const { return ws[(OFF_PIV + i) * PPB]; }
         OD_HD double& CP(int i) const { return ws[(OFF_CP + i) * PPB]; }
         OD_HD void sync() const {
 #ifdef __CUDA_ARCH__
@@ -221,7 +221,7 @@ struct ContactIP {
             int p = k; double best = fabs(L.K(k, k));
 #pragma unroll
             for (int i = k + 1; i < NR; ++i) { const double a = fabs(L.K(i, k)); if (a > best) { best = a; p = i; } }
-            L.piv[k] = p;
+            if (L.g == 0) L.PIV(k) = (double)p;
             ok = ok && (best > 0.0) && (best < INFINITY);
             if (G > 1) L.sync();                              // all lanes have read column k before rows move
             if (p != k) {
@@ -234,7 +234,6 @@ struct ContactIP {
             }
             if (G > 1) L.sync();
             const double inv = 1.0 / L.K(k, k);
-            L.ipiv[k] = inv;
             double prow[NR];
 #pragma unroll
             for (int j = k + 1; j < NR; ++j) prow[j] = L.K(k, j);
@@ -250,22 +249,25 @@ struct ContactIP {
                 }
             }
             if (G > 1) L.sync();
+            if (L.g == 0) L.K(k, k) = inv;                    // keep the reciprocal pivot (nobody reads (k,k) again before the solves)
         }
+        L.sync();
         L.ok = ok;
     }
 
     // x ← K⁻¹ x for one right-hand side held in registers; run redundantly by every lane that needs the result.
     // `scratch` is a workspace vector private to the calling lane (used only for the dynamic-index row interchanges).
     OD_HD static void lu_solve(const Lin& L, double* x, double* scratch) {
+        int piv[NR];
         bool any = false;
 #pragma unroll
-        for (int k = 0; k < NR; ++k) any = any || (L.piv[k] != k);
+        for (int k = 0; k < NR; ++k) { piv[k] = (int)L.PIV(k); any = any || (piv[k] != k); }
         if (any) {                                            // interchanges need run-time indexing: do them in the workspace
 #pragma unroll
             for (int i = 0; i < NR; ++i) scratch[i * PPB] = x[i];
 #pragma unroll
             for (int k = 0; k < NR; ++k) {
-                const int p = L.piv[k];
+                const int p = piv[k];
                 if (p != k) { const double t = scratch[k * PPB]; scratch[k * PPB] = scratch[p * PPB]; scratch[p * PPB] = t; }
             }
 #pragma unroll
@@ -280,7 +282,7 @@ struct ContactIP {
         for (int i = NR - 1; i >= 0; --i) {
 #pragma unroll
             for (int j = i + 1; j < NR; ++j) x[i] -= L.K(i, j) * x[j];
-            x[i] *= L.ipiv[i];
+            x[i] *= L.K(i, i);
         }
     }
 
@@ -608,7 +610,6 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
     }
     typename IP::Lin L;
     L.ws = ws; L.g = g; L.gmask = gmask; L.ok = true;
-    typename IP::R r;
     double r_vio = 0.0, k_vio = 0.0, alpha = 0.0;
     D = z;                                  // any finite values: the first candidate uses alpha = 0
     bool first = true, eval_done = !a.want_eval, grad_done = !a.want_grad;
@@ -622,7 +623,7 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
             alpha *= a.opts.ls_scale; ++ls;
             continue;
         }
-        z = zc; r = rc; r_vio = rv2; k_vio = kv2;
+        z = zc; r_vio = rv2; k_vio = kv2;
         if (!first) ++it;
         first = false;
         // ---- accepted iterate: termination tests ----------------------------------------------------------------------------
@@ -655,7 +656,7 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
         }
         if (!do_iter) break;
         if (!L.ok) { if (!eval_done) { st_e = ST_FAIL; it_e = it; } if (!grad_done) { st_g = ST_FAIL; it_g = it; } break; }
-        IP::direction(L, z, r, r_vio, k_vio, D, alpha);
+        IP::direction(L, z, rc, r_vio, k_vio, D, alpha);
         ls = 0;
     }
     if (g == 0) {

@@ -81,8 +81,22 @@ def emit_function(fname, inputs, outputs, doc=""):
         for i, s in enumerate(syms):
             if s in used:
                 lines.append("    const double %s = %s[%d];" % (s.name, aname, i))
-    for s, e in repl:
-        lines.append("    const double %s = %s;" % (s.name, PR.doprint(e)))
+    # pair sin(a)/cos(a) of the same argument into one sincos() call (one range reduction instead of two)
+    trig = {}
+    for s_, e in repl:
+        if e.func in (sp.sin, sp.cos):
+            trig.setdefault(e.args[0], {})[e.func] = s_
+    paired = {arg: d for arg, d in trig.items() if len(d) == 2}
+    emitted = set()
+    for s_, e in repl:
+        if e.func in (sp.sin, sp.cos) and e.args[0] in paired:
+            arg = e.args[0]
+            if arg not in emitted:
+                emitted.add(arg)
+                d = paired[arg]
+                lines.append("    double %s, %s; sincos(%s, &%s, &%s);" % (d[sp.sin].name, d[sp.cos].name, PR.doprint(arg), d[sp.sin].name, d[sp.cos].name))
+            continue
+        lines.append("    const double %s = %s;" % (s_.name, PR.doprint(e)))
     for (oname, i), e in zip(slots, red):
         lines.append("    %s[%d] = %s;" % (oname, i, PR.doprint(e)))
     lines.append("}")
