@@ -108,10 +108,10 @@ def cpu_baseline(B, seconds=10.0, pattern="D", nthreads=0):
     cores = O.num_threads() if nthreads <= 0 else nthreads
 
     def one_pass():
-        O.step_batch("hopper", q1, q2, u, H, KAPPA_EVAL, False, r_tol=R_TOL, nthreads=nthreads)
-        O.step_batch("hopper", q1, q2, u, H, KAPPA_GRAD, True, r_tol=R_TOL, nthreads=nthreads)
+        O.step_batch("hopper", q1, q2, u, H, KAPPA_EVAL, False, r_tol=R_TOL, nthreads=nthreads, diagnostics=False)
+        O.step_batch("hopper", q1, q2, u, H, KAPPA_GRAD, True, r_tol=R_TOL, nthreads=nthreads, diagnostics=False)
         if pattern == "R":
-            O.step_batch("hopper", q1, q2, u, H, KAPPA_GRAD, True, r_tol=R_TOL, nthreads=nthreads)
+            O.step_batch("hopper", q1, q2, u, H, KAPPA_GRAD, True, r_tol=R_TOL, nthreads=nthreads, diagnostics=False)
     one_pass()
     t0 = time.perf_counter(); n = 0
     while True:
@@ -138,9 +138,9 @@ def run_reference(args):
     q1, q2, u = W.hopper_batch(B, h=H, seed=0)
 
     def step():
-        O.step_batch("hopper", q1, q2, u, H, KAPPA_EVAL, False, r_tol=R_TOL)      # f
-        O.step_batch("hopper", q1, q2, u, H, KAPPA_GRAD, True, r_tol=R_TOL)       # fx
-        O.step_batch("hopper", q1, q2, u, H, KAPPA_GRAD, True, r_tol=R_TOL)       # fu (re-solves, src/dynamics.jl:123)
+        O.step_batch("hopper", q1, q2, u, H, KAPPA_EVAL, False, r_tol=R_TOL, diagnostics=False)      # f
+        O.step_batch("hopper", q1, q2, u, H, KAPPA_GRAD, True, r_tol=R_TOL, diagnostics=False)       # fx
+        O.step_batch("hopper", q1, q2, u, H, KAPPA_GRAD, True, r_tol=R_TOL, diagnostics=False)       # fu (re-solves, src/dynamics.jl:123)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()

@@ -493,7 +493,7 @@ struct ContactIP {
         if (L.g == 0) {
             double amax = 0.0;
             for (int i = 0; i < NR; ++i) for (int j = 0; j < NR; ++j) amax = fmax(amax, fabs(L.K(i, j)));
-            const double tol = 1e-11 * amax;
+            const double tol = 1e-13 * amax;      // exact redundancy leaves pivots at rounding level (≲1e-16·amax); κ-level pivots (≳1e-11) are genuine
             for (int k = 0; k < NR; ++k) {
                 int p = k, q = k; double best = -1.0;
                 for (int i = k; i < NR; ++i) for (int j = k; j < NR; ++j) { const double a = fabs(L.K(i, j)); if (a > best) { best = a; p = i; q = j; } }

@@ -40,6 +40,7 @@ struct Options {                         // RoboDojo InteriorPointOptions defaul
     int max_iter = 100, max_ls = 3;
     double eps_min = 0.05, kappa_reg = 1e-3, gamma_reg = 1e-1, undercut = 5.0;
     bool diff_sol = false;
+    bool diagnostics = false;   // tests only: also report how far the returned iterate is from the exact root (SolveInfo::q_uncertainty)
 };
 
 struct SolveInfo {
@@ -48,6 +49,8 @@ struct SolveInfo {
     int ls_steps = 0;          // total backtracking halvings
     double r_vio = 0, k_vio = 0;
     double margin = std::numeric_limits<double>::infinity();  // min relative distance of any discrete decision from flipping
+    double q_uncertainty = 0.0; // ‖(rz⁻¹ r(z*;θ,0))[output rows]‖∞: the next Newton step = distance of the returned q3 from the exact root.
+                                // The solver stops at the FIRST iterate inside the tolerances, so q3 is only defined up to this amount.
     double ift_spread = 0.0;   // max |δz − δz'| where δz' re-solves with rz's rows rescaled by powers of two (different pivot order, same
                                // exact solution): large ⇒ rz(z*) is numerically singular and the sensitivities are not determined in fp64
 };
@@ -234,6 +237,16 @@ struct InteriorPoint {
             if (!converged) info.status = 1;
         }
         info.r_vio = r_vio; info.k_vio = k_vio;
+        if (opts.diagnostics && info.status != 2) {
+            double rz2[NZ * NZ], st[NZ]; int pv[NZ];
+            eval_rz(z, rz2);
+            if (lu_factor(rz2, pv, NZ)) {
+                for (int i = 0; i < NZ; ++i) st[i] = r[i];
+                lu_solve(rz2, pv, NZ, st);
+                double m = 0.0; for (int i = 0; i < n_out_rows; ++i) m = std::max(m, std::fabs(st[i]));
+                info.q_uncertainty = m;
+            } else info.q_uncertainty = std::numeric_limits<double>::infinity();
+        }
         if (opts.diff_sol && info.status != 2) {
             if (!differentiate(&info.ift_spread)) info.status = 2;
         }

@@ -51,7 +51,7 @@ def residual(model, z, th, kappa=0.0):
     return r, rz, rth
 
 
-def step_batch(model, q1, q2, u, h, kappa_tol, diff, fric=None, r_tol=1e-8, nthreads=0, full=False):
+def step_batch(model, q1, q2, u, h, kappa_tol, diff, fric=None, r_tol=1e-8, nthreads=0, full=False, diagnostics=True):
     """Returns dict(q3, dq1, dq2, du (column-major per problem, as (B, ncol, nq) arrays), iters, status, ls, r_vio, k_vio, margin)."""
     mid = MODELS[model]
     nq, nu, nz, nth = dims(model)
@@ -59,7 +59,7 @@ def step_batch(model, q1, q2, u, h, kappa_tol, diff, fric=None, r_tol=1e-8, nthr
     q2 = np.ascontiguousarray(q2, dtype=np.float64).reshape(B, nq)
     u = np.ascontiguousarray(u, dtype=np.float64).reshape(B, nu)
     fr = None if fric is None else np.ascontiguousarray(fric, dtype=np.float64)
-    q3 = np.zeros((B, nq)); info = np.zeros((B, 4), dtype=np.int32); vio = np.zeros((B, 4))
+    q3 = np.zeros((B, nq)); info = np.zeros((B, 4), dtype=np.int32); vio = np.zeros((B, 5)) if diagnostics else None
     dq1 = dq2 = du = dzf = None
     if diff:
         dq1 = np.zeros((B, nq, nq)); dq2 = np.zeros((B, nq, nq)); du = np.zeros((B, nu, nq))
@@ -69,8 +69,10 @@ def step_batch(model, q1, q2, u, h, kappa_tol, diff, fric=None, r_tol=1e-8, nthr
     rc = lib().od_oracle_step_batch(mid, B, _p(q1), _p(q2), _p(u), _p(fr), C.c_double(h), C.c_double(r_tol), C.c_double(kappa_tol),
                                     int(bool(diff)), _p(q3), _p(dq1), _p(dq2), _p(du), _p(dzf), _p(zout), _p(info, C.c_int), _p(vio), int(nthreads))
     assert rc == 0
-    return dict(q3=q3, dq1=dq1, dq2=dq2, du=du, dz_full=dzf, z=zout, iters=info[:, 0].copy(), status=info[:, 1].copy(), ls=info[:, 2].copy(),
-                r_vio=vio[:, 0].copy(), k_vio=vio[:, 1].copy(), margin=vio[:, 2].copy(), ift_spread=vio[:, 3].copy())
+    out = dict(q3=q3, dq1=dq1, dq2=dq2, du=du, dz_full=dzf, z=zout, iters=info[:, 0].copy(), status=info[:, 1].copy(), ls=info[:, 2].copy())
+    if diagnostics:
+        out.update(r_vio=vio[:, 0].copy(), k_vio=vio[:, 1].copy(), margin=vio[:, 2].copy(), ift_spread=vio[:, 3].copy(), q_uncertainty=vio[:, 4].copy())
+    return out
 
 
 def rocket_batch(x, u, h, u_max, proj, diff, nthreads=0):

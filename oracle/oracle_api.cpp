@@ -234,19 +234,20 @@ int od_oracle_residual(int model, const double* z, const double* th, double kapp
 
 // Batched step (+ optional IFT).  diff=0: eval solve only (f).  diff=1: grad solve (fx/fu).  Any output pointer may be NULL.
 // q1,q2: B×nq, u: B×nu (row per problem).  Jacobians column-major per problem.  info: B×4 = [iterations, status, ls_steps, _],
-// vio: B×4 = [r_vio, κ_vio, margin, ift_spread].  dz_full: B×nz×nθ row-major (tests only).  z_out: B×nz.
+// vio: B×5 = [r_vio, κ_vio, margin, ift_spread, q_uncertainty].  dz_full: B×nz×nθ row-major (tests only).  z_out: B×nz.
 int od_oracle_step_batch(int model, int B, const double* q1, const double* q2, const double* u, const double* fric, double h,
                          double r_tol, double kappa_tol, int diff,
                          double* q3, double* dq1, double* dq2, double* du, double* dz_full, double* z_out, int* info, double* vio, int nthreads) {
     Dims d; if (!dims_of(model, &d) || model >= ROCKET) return 1;
     Options o = contact_opts(r_tol, kappa_tol, diff != 0);
+    o.diagnostics = (vio != nullptr);
     parallel_for(B, nthreads, 16, [&](int i) {
         SolveInfo s = step_model(model, o, q1 + (size_t)i * d.nq, q2 + (size_t)i * d.nq, u + (size_t)i * d.nu, fric, h,
                                  q3 ? q3 + (size_t)i * d.nq : nullptr, dq1 ? dq1 + (size_t)i * d.nq * d.nq : nullptr,
                                  dq2 ? dq2 + (size_t)i * d.nq * d.nq : nullptr, du ? du + (size_t)i * d.nq * d.nu : nullptr,
                                  dz_full ? dz_full + (size_t)i * d.nz * d.nth : nullptr, z_out ? z_out + (size_t)i * d.nz : nullptr);
         if (info) { info[4 * i] = s.iterations; info[4 * i + 1] = s.status; info[4 * i + 2] = s.ls_steps; info[4 * i + 3] = 0; }
-        if (vio) { vio[4 * i] = s.r_vio; vio[4 * i + 1] = s.k_vio; vio[4 * i + 2] = s.margin; vio[4 * i + 3] = s.ift_spread; }
+        if (vio) { vio[5 * i] = s.r_vio; vio[5 * i + 1] = s.k_vio; vio[5 * i + 2] = s.margin; vio[5 * i + 3] = s.ift_spread; vio[5 * i + 4] = s.q_uncertainty; }
     });
     return 0;
 }

@@ -24,7 +24,8 @@ for name, (gen, h, ke, kg, fric, _) in CONFIGS.items():
     g = O.step_batch(name, q1, q2, u, h, kg, True, fric=fric)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), q1=q1, q2=q2, u=u, q3=e["q3"], dq1=g["dq1"], dq2=g["dq2"], du=g["du"],
                         status_eval=e["status"], status_grad=g["status"], iters_eval=e["iters"], iters_grad=g["iters"],
-                        margin=np.minimum(e["margin"], g["margin"]), ift_spread=g["ift_spread"])
+                        margin=np.minimum(e["margin"], g["margin"]), ift_spread=g["ift_spread"],
+                        q_uncertainty=np.maximum(e["q_uncertainty"], g["q_uncertainty"]))
 x, u = W.rocket_batch(B, seed=2024)
 for proj, name in ((False, "rocket"), (True, "rocket_proj")):
     r = O.rocket_batch(x, u, 0.05, 12.5, proj, True)
