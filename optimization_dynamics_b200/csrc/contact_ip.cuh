@@ -87,7 +87,9 @@ struct ContactIP {
     static constexpr int OFF_X = NR * NRP;               // NTP right-hand-side / solution vectors, pitch NRP (odd: lane-private vectors on disjoint banks)
     static constexpr int OFF_PIV = OFF_X + NTP * NRP;    // row interchanges of the LU (LAPACK convention), stored as doubles
     static constexpr int OFF_CP = OFF_PIV + NR;          // column permutation of the rank-revealing factorisation (robust IFT only)
-    static constexpr int WS = OFF_CP + (M::ROBUST_IFT ? NR : 0);   // workspace doubles per problem
+    static constexpr int NZ = NQ + 2 * NC + 2 * NP + 2 * NB;
+    static constexpr int OFF_ZS = OFF_CP + (M::ROBUST_IFT ? NR : 0);   // snapshot of the iterate at which the IFT is taken
+    static constexpr int WS = OFF_ZS + NZ;               // workspace doubles per problem
 
     struct Z { double q[NQ], gam[NC1], s[NC1], psi[NP1], b[NB1], spsi[NP1], sb[NB1]; };
     // residual in block form; bilinear rows are stored at κ = 0 (r(z;κ) only shifts rgam and rc0 by −κ)
@@ -529,6 +531,32 @@ struct ContactIP {
         return rank > 0;
     }
 
+    // iterate ↔ workspace snapshot (all lanes of a group write identical values)
+    OD_HD static void store_z(const Lin& L, const Z& z) {
+        double* p = &L.ws[OFF_ZS * PPB];
+        int e = 0;
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) p[(e++) * PPB] = z.q[i];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) { p[(e++) * PPB] = z.gam[i]; p[(e++) * PPB] = z.s[i]; }
+#pragma unroll
+        for (int i = 0; i < NP; ++i) { p[(e++) * PPB] = z.psi[i]; p[(e++) * PPB] = z.spsi[i]; }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) { p[(e++) * PPB] = z.b[i]; p[(e++) * PPB] = z.sb[i]; }
+    }
+    OD_HD static void load_z(const Lin& L, Z& z) {
+        const double* p = &L.ws[OFF_ZS * PPB];
+        int e = 0;
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) z.q[i] = p[(e++) * PPB];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) { z.gam[i] = p[(e++) * PPB]; z.s[i] = p[(e++) * PPB]; }
+#pragma unroll
+        for (int i = 0; i < NP; ++i) { z.psi[i] = p[(e++) * PPB]; z.spsi[i] = p[(e++) * PPB]; }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) { z.b[i] = p[(e++) * PPB]; z.sb[i] = p[(e++) * PPB]; }
+    }
+
     // initialize_z! (reference src/models/planar_push/simulator.jl:52-60 and the same pattern in the other models)
     OD_HD static void init_z(const double* q2, Z& z) {
 #pragma unroll
@@ -640,24 +668,29 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
                 for (int k = 0; k < NQ; ++k) o[k] = z.q[k];
             }
         }
-        const bool need_ift = !grad_done && (conv_g || capped || bad);
-        const bool do_iter = !bad && !capped && (!eval_done || (!grad_done && !need_ift));
-        if (!need_ift && !do_iter) break;
-        if (M::ROBUST_IFT && need_ift) {
-            IP::assemble(z, th, L);
-            bool okr = true;
-            if (a.dq1) okr = IP::sensitivities_robust(L, z, th, a.dq1 + (size_t)i * a.out_stride_dq, a.dq2 + (size_t)i * a.out_stride_dq, a.du + (size_t)i * a.out_stride_du);
-            grad_done = true; it_g = it; st_g = (bad || !okr) ? ST_FAIL : (conv_g ? ST_OK : ST_MAXIT);
+        if (!grad_done && (conv_g || capped || bad)) {           // the IFT itself is deferred until the loop has finished
+            grad_done = true; it_g = it; st_g = bad ? ST_FAIL : (conv_g ? ST_OK : ST_MAXIT);
+            IP::store_z(L, z);
         }
-        if (do_iter || (need_ift && !M::ROBUST_IFT)) IP::linearize(z, th, L);
-        if (need_ift && !M::ROBUST_IFT) {
-            grad_done = true; it_g = it; st_g = (bad || !L.ok) ? ST_FAIL : (conv_g ? ST_OK : ST_MAXIT);
-            if (a.dq1) IP::sensitivities(L, z, th, a.dq1 + (size_t)i * a.out_stride_dq, a.dq2 + (size_t)i * a.out_stride_dq, a.du + (size_t)i * a.out_stride_du);
-        }
-        if (!do_iter) break;
-        if (!L.ok) { if (!eval_done) { st_e = ST_FAIL; it_e = it; } if (!grad_done) { st_g = ST_FAIL; it_g = it; } break; }
+        if (bad || capped || (eval_done && grad_done)) break;
+        IP::linearize(z, th, L);
+        if (!L.ok) { if (!eval_done) { st_e = ST_FAIL; it_e = it; } if (!grad_done) { st_g = ST_FAIL; it_g = it; IP::store_z(L, z); grad_done = true; } break; }
         IP::direction(L, z, rc, r_vio, k_vio, D, alpha);
         ls = 0;
+    }
+    // ---- IFT at the snapshot.  It sits after the loop on purpose: the problems of a warp converge at different iterations, and a
+    // sensitivity pass inside the loop would be executed once per distinct convergence iteration (up to 8× per warp).
+    if (a.want_grad && a.dq1) {
+        IP::load_z(L, z);
+        double* o1 = a.dq1 + (size_t)i * a.out_stride_dq; double* o2 = a.dq2 + (size_t)i * a.out_stride_dq; double* o3 = a.du + (size_t)i * a.out_stride_du;
+        if (M::ROBUST_IFT) {
+            IP::assemble(z, th, L);
+            if (!IP::sensitivities_robust(L, z, th, o1, o2, o3)) st_g = ST_FAIL;
+        } else {
+            IP::linearize(z, th, L);
+            if (!L.ok) st_g = ST_FAIL;
+            IP::sensitivities(L, z, th, o1, o2, o3);
+        }
     }
     if (g == 0) {
         if (a.status) a.status[i] = st_e | (st_g << 4);
