@@ -169,6 +169,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extra", action="store_true", help="also report a saturating batch (262144 per GPU) in the JSON line")
+    ap.add_argument("--collective", default="fused", choices=["fused", "nccl"],
+                    help="N>1: 'fused' = all-gather fused into the kernel over NVLink peer memory (falls back to nccl if symmetric memory "
+                         "is unavailable); 'nccl' = kernel + ncclAllGather")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 200 and args.warmup == 10:
@@ -180,7 +183,7 @@ def main():
     import torch
     import torch.distributed as dist
     import optimization_dynamics_b200 as od
-    from optimization_dynamics_b200.device import DeviceStepper, all_gather_rows
+    from optimization_dynamics_b200.device import DeviceStepper, FusedGather, all_gather_rows, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -206,8 +209,22 @@ def main():
     status = torch.empty((B,), dtype=torch.int32, device=dev)
     gathered = torch.empty((B_total, stepper.out_width), dtype=torch.float64, device=dev) if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # 2× the 126 MB L2
+    fused = None
+    if world > 1 and args.collective == "fused":
+        okf = torch.ones(1, device=dev)
+        try:
+            fused = FusedGather(stepper, B_total)
+        except Exception as ex:                       # symmetric memory unavailable: every rank must take the same path
+            sys.stderr.write("rank %d: fused gather unavailable (%r), using ncclAllGather\n" % (rank, ex))
+            okf.zero_()
+        dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+        if okf.item() == 0:
+            fused = None
 
     def step():
+        if fused is not None:
+            fused.step(xin, status)
+            return
         stepper.step_grad_packed(xin, out, status)
         if world > 1:
             all_gather_rows(out, B_total, gathered)
@@ -231,10 +248,15 @@ def main():
     for k in range(args.steps):
         flush.zero_()
         starts[k].record()
-        stepper.step_grad_packed(xin, out, status)
-        kmid[k].record()
-        if world > 1:
-            all_gather_rows(out, B_total, gathered)
+        if fused is not None:
+            fused.launch(xin, status)
+            kmid[k].record()
+            fused.barrier()
+        else:
+            stepper.step_grad_packed(xin, out, status)
+            kmid[k].record()
+            if world > 1:
+                all_gather_rows(out, B_total, gathered)
         ends[k].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -244,6 +266,19 @@ def main():
     ker_ms = sum(s.elapsed_time(e) for s, e in zip(starts, kmid))
     ok_frac = float((status == 0).float().mean().item())
 
+    gather_check = None
+    if world > 1:
+        # the rows every rank now holds must be bit-identical to a plain ncclAllGather of the per-rank results
+        stepper.step_grad_packed(xin, out, status)
+        ref = all_gather_rows(out, B_total)
+        if fused is not None:
+            got, _ = fused.step(xin, status)
+            torch.cuda.synchronize()
+            gather_check = bool(torch.equal(got, ref))
+            assert gather_check, "fused gather differs from ncclAllGather"
+        lo, hi = shard_range(B_total, rank, world)
+        assert torch.equal(ref[lo:hi], out)
+        out_dev_result = out
     # ---- end-to-end through the public host API: pinned host in/out, H2D + kernel + D2H every step -----------------------------
     out_host = torch.empty((B, stepper.out_width), dtype=torch.float64).pin_memory()
     st_host = torch.empty((B,), dtype=torch.int32).pin_memory()
@@ -294,7 +329,10 @@ def main():
             "config": {"workload": "hopper gait contact step + IFT gradient (RoboDojo hopper, nq=4, nz=20), batch %d per GPU, h=0.05, "
                                    "kappa_eval=1e-4, kappa_grad=1e-3, r_tol=1e-8 (BASELINE.json configs[3])" % B,
                        "batch_per_gpu": B, "global_batch": B_total, "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
-                       "collective": "ncclAllGather of 352-B rows" if world > 1 else "none (1 GPU)", "converged_fraction": ok_frac},
+                       "collective": ("none (1 GPU)" if world == 1 else
+                                      "all-gather fused into the kernel: P2P stores of each finished 352-B row into every rank's buffer over NVLink + symmetric-memory barrier"
+                                      if fused is not None else "kernel + ncclAllGather of 352-B rows"),
+                       "gather_check_bitwise_equal_to_nccl": gather_check, "converged_fraction": ok_frac},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                          "kernel": "od::contact_step_kernel<HopperModel,32>", "kernel_ms": ker_ms_per, "algorithmic_bytes_per_launch": (BYTES_IN + BYTES_OUT) * B,
                          "peak_source": peak_src,

@@ -82,6 +82,15 @@ int od_step_grad_batch_device(od_handle* hd, int B, const double* q1, const doub
 int od_step_grad_packed_device(od_handle* hd, int B, const double* in, double* out, int32_t* status, int32_t* iters,
                                int want_eval, int want_grad);
 
+/* Multi-GPU derivative sweep with the all-gather fused into the kernel (single node, NVLink/NVSwitch peer access).
+ * Every rank solves its contiguous shard [row0, row0+B) of the global batch and stores each finished packed output row into the
+ * gather buffer of EVERY rank: gather_buffers[r] is rank r's [B_total × (nq + nq(2nq+nu))] buffer as mapped in THIS process
+ * (peer-mapped device pointers, e.g. from torch symmetric memory / cudaIpcOpenMemHandle); world ≤ 8.  Asynchronous; the caller
+ * must run a cross-rank barrier after the kernel before reading rows produced by other ranks.  Replaces kernel + ncclAllGather
+ * (the Jacobians the sequential Riccati pass needs). */
+int od_step_grad_packed_gather_device(od_handle* hd, int B, const double* in, long long row0, int world, int rank,
+                                      const uint64_t* gather_buffers, int32_t* status, int32_t* iters);
+
 /* Gradient bundle — gradient!(eval_sim, gb, q1, q2, u1), reference src/gradient_bundle.jl:87-104: one nominal and N perturbed
  * eval-sim steps per problem ((N+1)·B solves in one launch), then the least-squares fit of src/ls.jl:44-60 in closed form
  * (normal equations).  eta: N×(2nq+nu) perturbations shared by the batch (host).  dz: B×(nq×(2nq+nu)) column-major (host).

@@ -598,6 +598,13 @@ struct StepArgs {
     // gradient bundle (reference src/gradient_bundle.jl:89-100): problem i = sample i/(n_eta+1) perturbed by eta row i%(n_eta+1) − 1
     // (row −1 = nominal); eta is n_eta × (2NQ+NU), null when unused.
     const double* eta; int n_eta;
+    // Fused all-gather (multi-GPU): when n_peers > 1 the packed output row of problem i is also stored into the gather buffers of
+    // the other ranks (peer-mapped device pointers, NVLink P2P) as soon as the problem has finished — the transfer overlaps the
+    // remaining problems' compute and replaces the separate ncclAllGather.  `gather_row0` = first row of this rank's shard,
+    // `gather_width` = doubles per row; the local outputs (q3/dq1/dq2/du) must already point into this rank's own gather buffer.
+    int n_peers, self_rank;
+    long long gather_row0; int gather_width;
+    double* peer_out[8];
     SolverOpts opts;
 };
 
@@ -692,6 +699,17 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
             IP::sensitivities(L, z, th, o1, o2, o3);
         }
     }
+#ifdef __CUDA_ARCH__
+    if (a.n_peers > 1) {
+        L.sync();                                              // every lane's share of the row has been written
+        const size_t off = (size_t)(a.gather_row0 + i) * a.gather_width;
+        const double* row = a.peer_out[a.self_rank] + off;
+        for (int k = g; k < a.gather_width; k += G) {
+            const double v = __ldcg(row + k);
+            for (int p = 0; p < a.n_peers; ++p) if (p != a.self_rank) a.peer_out[p][off + k] = v;
+        }
+    }
+#endif
     if (g == 0) {
         if (a.status) a.status[i] = st_e | (st_g << 4);
         if (a.iters) a.iters[i] = it_e | (it_g << 16);

@@ -244,6 +244,24 @@ int od_step_grad_packed_device(od_handle* hd, int B, const double* in, double* o
     return launch_step(hd, a);
 }
 
+int od_step_grad_packed_gather_device(od_handle* hd, int B, const double* in, long long row0, int world, int rank,
+                                      const uint64_t* gather_buffers, int32_t* status, int32_t* iters) {
+    if (!hd) return fail("null handle");
+    if (world < 1 || world > 8 || rank < 0 || rank >= world || !gather_buffers) return fail("od_step_grad_packed_gather_device: need 1 <= world <= 8 and the peer buffer table");
+    Dims d; dims_of(hd->model, &d);
+    OD_CUDA(cudaSetDevice(hd->device));
+    const int inw = 2 * d.nq + d.nu, outw = d.nq + d.nq * inw;
+    double* out = (double*)gather_buffers[rank] + (size_t)row0 * outw;
+    StepArgs a; memset(&a, 0, sizeof(a));
+    a.B = B; a.q1 = in; a.q2 = in + d.nq; a.u = in + 2 * d.nq; a.in_stride_q = inw; a.in_stride_u = inw;
+    a.q3 = out; a.dq1 = out + d.nq; a.dq2 = out + d.nq + d.nq * d.nq; a.du = out + d.nq + 2 * d.nq * d.nq;
+    a.out_stride_q3 = outw; a.out_stride_dq = outw; a.out_stride_du = outw;
+    a.status = status; a.iters = iters; a.want_eval = 1; a.want_grad = 1;
+    a.n_peers = world; a.self_rank = rank; a.gather_row0 = row0; a.gather_width = outw;
+    for (int r = 0; r < world; ++r) a.peer_out[r] = (double*)gather_buffers[r];
+    return launch_step(hd, a);
+}
+
 int od_step_grad_packed(od_handle* hd, int B, const double* in, double* out, int32_t* status) {
     if (!hd) return fail("null handle");
     Dims d; dims_of(hd->model, &d);

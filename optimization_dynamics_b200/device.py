@@ -84,6 +84,47 @@ class DeviceStepper:
         return all_gather_rows(out_local, B_total, gathered), status
 
 
+class FusedGather:
+    """All-gather fused into the step kernel over NVLink peer memory (torch symmetric memory supplies the peer-mapped buffers).
+
+    Every rank owns a [B_total, out_width] gather buffer; the kernel stores each finished 352-B row (hopper) into all of them, so
+    the exchange overlaps the compute of the problems still iterating; a symmetric-memory barrier replaces the NCCL collective."""
+
+    def __init__(self, stepper: DeviceStepper, B_total, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.stepper, self.B_total = stepper, B_total
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        if self.world > 8:
+            raise RuntimeError("FusedGather: single node, at most 8 ranks")
+        self.buf = symm_mem.empty((B_total, stepper.out_width), dtype=torch.float64, device=torch.device("cuda", torch.cuda.current_device()))
+        self.handle = symm_mem.rendezvous(self.buf, dist.group.WORLD if group is None else group)
+        self.ptrs = (C.c_uint64 * self.world)(*[int(p) for p in self.handle.buffer_ptrs])
+        self.row0 = shard_range(B_total, self.rank, self.world)[0]
+
+    def step(self, xin_local, status=None, iters=None):
+        """Asynchronous on torch's current stream; returns the gathered [B_total, out_width] tensor (valid after the barrier that
+        this call enqueues)."""
+        status = self.launch(xin_local, status, iters)
+        self.barrier()
+        return self.buf, status
+
+    def barrier(self):
+        self.handle.barrier(channel=0)
+
+    def launch(self, xin_local, status=None, iters=None):
+        t = self.stepper.torch
+        B = xin_local.shape[0]
+        if status is None:
+            status = t.empty((B,), dtype=t.int32, device=xin_local.device)
+        self.stepper._bind_stream()
+        _lib.check(_lib.lib().od_step_grad_packed_gather_device(
+            self.stepper.dyn._handle(), B, C.c_void_p(xin_local.data_ptr()), self.row0, self.world, self.rank, self.ptrs,
+            C.c_void_p(status.data_ptr()), C.c_void_p(iters.data_ptr()) if iters is not None else None))
+        return status
+
+
 def unpack_outputs(out, nq, nu):
     """Split packed rows into q3 [B,nq] and Jacobians [B,nq,nq], [B,nq,nq], [B,nq,nu] (row = q3 component).  numpy or torch."""
     B = out.shape[0]
