@@ -80,6 +80,7 @@ template <class M, int G = 1, int PPB = 1>
 struct ContactIP {
     static constexpr int NQ = M::NQ, NU = M::NU, NC = M::NC, NP = M::NP, NB = M::NB, NTH = M::NTH;
     static constexpr int NC1 = cmax1<NC>::v, NP1 = cmax1<NP>::v, NB1 = cmax1<NB>::v;
+    static constexpr int NTC1 = cmax1<M::NTC>::v, NTV1 = cmax1<M::NTV>::v;   // sin/cos tables (θ-only / q-dependent arguments)
     static constexpr int NTP = 2 * NQ + NU;              // θ' = (q1, q2, u): the sensitivity columns that are returned
     static constexpr int NCONE = NC + NP;                // cone degree (orthant pairs + second-order cones)
     static constexpr int NR = NQ + NC + NB + NP;         // reduced system size
@@ -117,9 +118,9 @@ struct ContactIP {
     }
 
     // ---- residual ------------------------------------------------------------------------------------------------
-    OD_HD static void residual(const Z& z, const double* th, R& r, double& r_vio, double& k_vio) {
+    OD_HD static void residual(const Z& z, const double* th, const double* trc, const double* trv, R& r, double& r_vio, double& k_vio) {
         double phi[NC1], psit[NP1], vT[NB1];
-        M::eq(z.q, z.gam, z.b, th, r.d, phi, psit, vT);
+        M::eq(z.q, z.gam, z.b, th, trc, trv, r.d, phi, psit, vT);
         double rv = 0.0, kv = 0.0;
 #pragma unroll
         for (int i = 0; i < NQ; ++i) rv = fmax(rv, fabs(r.d[i]));
@@ -156,12 +157,12 @@ struct ContactIP {
     //   γ_i  : γ_i N_i Δq + s_i Δγ_i                                             = rgam_i − γ_i rs_i
     //   c0_k : (Σ_j b_j V_j) Δq + sψ_k Mψ_k Δγ + Σ_j sb_j Δb_j + ψ_k Δsψ_k        = rc0_k − sψ_k rpsi_k + Σ_j b_j rv_j
     //   c1_j : ψ_k V_j Δq + sb_j Mψ_k Δγ + sψ_k Δb_j + b_j Δsψ_k                  = rc1_j − sb_j rpsi_k + ψ_k rv_j
-    OD_HD static void linearize(const Z& z, const double* th, Lin& L) { assemble(z, th, L); factor(L); }
+    OD_HD static void linearize(const Z& z, const double* th, const double* trc, const double* trv, Lin& L) { assemble(z, th, trc, trv, L); factor(L); }
     // every lane of the group writes the same values (benign); factor() synchronises before reading
-    OD_HD static void assemble(const Z& z, const double* th, Lin& L) {
+    OD_HD static void assemble(const Z& z, const double* th, const double* trc, const double* trv, Lin& L) {
         static_assert(NTP >= G, "each lane needs a private scratch vector");
         double D[NQ * NQ], Eg[NQ * NC1], Eb[NQ * NB1];
-        M::jac(z.q, z.gam, z.b, th, D, Eg, Eb, L.N, L.V, L.Mpsi);
+        M::jac(z.q, z.gam, z.b, th, trc, trv, D, Eg, Eb, L.N, L.V, L.Mpsi);
         L.sync();                                             // no lane may still be reading the previous factorisation
 #pragma unroll
         for (int i = 0; i < NQ; ++i) {
@@ -424,10 +425,10 @@ struct ContactIP {
     // ---- IFT: ∂q3/∂θ' = −(rz⁻¹ rθ')[q rows]; column c of the NQ×NTP column-major result goes to dq1 / dq2 / du ---------
     // The NTP reduced right-hand sides are written to the workspace (redundantly by all lanes), then lane g solves columns
     // g, g+G, … with the factorisation of rz at the final iterate.
-    OD_HD static void sensitivities(const Lin& L, const Z& z, const double* th, double* dq1, double* dq2, double* du) {
+    OD_HD static void sensitivities(const Lin& L, const Z& z, const double* th, const double* trc, const double* trv, double* dq1, double* dq2, double* du) {
         {
             double Dth[NQ * NTP], Vth[NB1 * NTP];
-            M::jacth(z.q, z.gam, z.b, th, Dth, Vth);
+            M::jacth(z.q, z.gam, z.b, th, trc, trv, Dth, Vth);
             R r;
 #pragma unroll
             for (int i = 0; i < NC1; ++i) { r.rs[i] = 0.0; r.rgam[i] = 0.0; }
@@ -467,10 +468,10 @@ struct ContactIP {
     // q rows of δz stay well defined.  Partial pivoting then divides by rounding-level pivots (or hits an exact zero); here the
     // factorisation at the final iterate uses COMPLETE pivoting, stops at the numerical rank, and solves the consistent system
     // with the free multipliers set to zero.  Runs once per problem, on lane 0 of the group (dynamic loops: small code).
-    OD_HD static bool sensitivities_robust(Lin& L, const Z& z, const double* th, double* dq1, double* dq2, double* du) {
+    OD_HD static bool sensitivities_robust(Lin& L, const Z& z, const double* th, const double* trc, const double* trv, double* dq1, double* dq2, double* du) {
         {
             double Dth[NQ * NTP], Vth[NB1 * NTP];
-            M::jacth(z.q, z.gam, z.b, th, Dth, Vth);
+            M::jacth(z.q, z.gam, z.b, th, trc, trv, Dth, Vth);
             R r;
 #pragma unroll
             for (int i = 0; i < NC1; ++i) { r.rs[i] = 0.0; r.rgam[i] = 0.0; }
@@ -645,6 +646,8 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
     }
     typename IP::Lin L;
     L.ws = ws; L.g = g; L.gmask = gmask; L.ok = true;
+    double trc[IP::NTC1], trv[IP::NTV1];            // sin/cos of the θ-only arguments (once) and of the q-dependent ones (per candidate)
+    M::trig_const(th, trc);
     double r_vio = 0.0, k_vio = 0.0, alpha = 0.0;
     D = z;                                  // any finite values: the first candidate uses alpha = 0
     bool first = true, eval_done = !a.want_eval, grad_done = !a.want_grad;
@@ -653,7 +656,8 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
         // ---- candidate z − αΔ and its residual (the only residual call site) ----------------------------------------------
         typename IP::R rc; double rv2, kv2;
         IP::candidate(z, D, alpha, zc);
-        IP::residual(zc, th, rc, rv2, kv2);
+        M::trig_var(zc.q, th, trv);
+        IP::residual(zc, th, trc, trv, rc, rv2, kv2);
         if (!(first || rv2 <= r_vio || kv2 <= k_vio || ls >= a.opts.max_ls)) {   // residual line search: halve and retry
             alpha *= a.opts.ls_scale; ++ls;
             continue;
@@ -680,7 +684,7 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
             IP::store_z(L, z);
         }
         if (bad || capped || (eval_done && grad_done)) break;
-        IP::linearize(z, th, L);
+        IP::linearize(z, th, trc, trv, L);                       // trv still belongs to z (the candidate that was just accepted)
         if (!L.ok) { if (!eval_done) { st_e = ST_FAIL; it_e = it; } if (!grad_done) { st_g = ST_FAIL; it_g = it; IP::store_z(L, z); grad_done = true; } break; }
         IP::direction(L, z, rc, r_vio, k_vio, D, alpha);
         ls = 0;
@@ -689,14 +693,15 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
     // sensitivity pass inside the loop would be executed once per distinct convergence iteration (up to 8× per warp).
     if (a.want_grad && a.dq1) {
         IP::load_z(L, z);
+        M::trig_var(z.q, th, trv);
         double* o1 = a.dq1 + (size_t)i * a.out_stride_dq; double* o2 = a.dq2 + (size_t)i * a.out_stride_dq; double* o3 = a.du + (size_t)i * a.out_stride_du;
         if (M::ROBUST_IFT) {
-            IP::assemble(z, th, L);
-            if (!IP::sensitivities_robust(L, z, th, o1, o2, o3)) st_g = ST_FAIL;
+            IP::assemble(z, th, trc, trv, L);
+            if (!IP::sensitivities_robust(L, z, th, trc, trv, o1, o2, o3)) st_g = ST_FAIL;
         } else {
-            IP::linearize(z, th, L);
+            IP::linearize(z, th, trc, trv, L);
             if (!L.ok) st_g = ST_FAIL;
-            IP::sensitivities(L, z, th, o1, o2, o3);
+            IP::sensitivities(L, z, th, trc, trv, o1, o2, o3);
         }
     }
 #ifdef __CUDA_ARCH__

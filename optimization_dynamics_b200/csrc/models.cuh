@@ -18,16 +18,20 @@ namespace od {
 #define OD_CONTACT_MODEL(NAME, NS, NFRIC, OFF_EXPR, DIM_EXPR, ROBUST)                                                                     \
     struct NAME {                                                                                                                \
         static constexpr int NQ = NS::NQ, NU = NS::NU, NC = NS::NC, NP = NS::NP, NB = NS::NB, NTH = NS::NTH, NF = NFRIC;           \
+        static constexpr int NTC = NS::NTC, NTV = NS::NTV;   /* sin/cos table sizes: θ-only and q-dependent arguments */          \
         static constexpr bool ROBUST_IFT = ROBUST;   /* redundant contact constraints: rank-revealing IFT (contact_ip.cuh) */  \
-        OD_HD static constexpr int cone_off(int k) { return OFF_EXPR; }                                             \
-        OD_HD static constexpr int cone_dim(int k) { return DIM_EXPR; }                                             \
-        OD_HD static void eq(const double* q, const double* g, const double* b, const double* th, double* d,  \
-                                                  double* phi, double* psit, double* vT) { NS::eq(q, g, b, th, d, phi, psit, vT); } \
-        OD_HD static void jac(const double* q, const double* g, const double* b, const double* th, double* D, \
-                                                   double* Eg, double* Eb, double* N, double* V, double* Mpsi) {                  \
-            NS::jac(q, g, b, th, D, Eg, Eb, N, V, Mpsi); }                                                                        \
-        OD_HD static void jacth(const double* q, const double* g, const double* b, const double* th,          \
-                                                     double* Dth, double* Vth) { NS::jacth(q, g, b, th, Dth, Vth); }              \
+        __host__ __device__ static constexpr int cone_off(int k) { return OFF_EXPR; }                                             \
+        __host__ __device__ static constexpr int cone_dim(int k) { return DIM_EXPR; }                                             \
+        OD_HD static void trig_const(const double* th, double* trc) { NS::trig_const(th, trc); }                                  \
+        OD_HD static void trig_var(const double* q, const double* th, double* trv) { NS::trig_var(q, th, trv); }                  \
+        OD_HD static void eq(const double* q, const double* g, const double* b, const double* th, const double* trc,              \
+                             const double* trv, double* d, double* phi, double* psit, double* vT) {                             \
+            NS::eq(q, g, b, th, trc, trv, d, phi, psit, vT); }                                                                    \
+        OD_HD static void jac(const double* q, const double* g, const double* b, const double* th, const double* trc,             \
+                              const double* trv, double* D, double* Eg, double* Eb, double* N, double* V, double* Mpsi) {       \
+            NS::jac(q, g, b, th, trc, trv, D, Eg, Eb, N, V, Mpsi); }                                                              \
+        OD_HD static void jacth(const double* q, const double* g, const double* b, const double* th, const double* trc,           \
+                                const double* trv, double* Dth, double* Vth) { NS::jacth(q, g, b, th, trc, trv, Dth, Vth); }      \
     };
 
 // cone k of the friction block: offset into b / sb and number of tangential components

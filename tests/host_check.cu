@@ -54,7 +54,9 @@ template <class M> static void resid_t(const double* zz, const double* th, doubl
     for (int i = 0; i < M::NB; ++i) z.b[i] = *p++;
     for (int i = 0; i < M::NP; ++i) z.spsi[i] = *p++;
     for (int i = 0; i < M::NB; ++i) z.sb[i] = *p++;
-    IP::residual(z, th, r, rv, kv);
+    double trc[IP::NTC1], trv[IP::NTV1];
+    M::trig_const(th, trc); M::trig_var(z.q, th, trv);
+    IP::residual(z, th, trc, trv, r, rv, kv);
     double* o = out;
     for (int i = 0; i < M::NQ; ++i) *o++ = r.d[i];
     for (int i = 0; i < M::NC; ++i) *o++ = r.rs[i];
@@ -65,7 +67,7 @@ template <class M> static void resid_t(const double* zz, const double* th, doubl
     for (int i = 0; i < M::NB; ++i) *o++ = r.rc1[i];
     typename IP::Lin L; typename IP::Z D; double ws[IP::WS];
     L.ws = ws; L.g = 0; L.gmask = 0u;
-    IP::linearize(z, th, L);
+    IP::linearize(z, th, trc, trv, L);
     IP::solve(L, z, r, D);
     o = dir;
     for (int i = 0; i < M::NQ; ++i) *o++ = D.q[i];
@@ -103,8 +105,10 @@ template <class M> static void sens_t(const double* zz, const double* th, double
     for (int i = 0; i < M::NB; ++i) z.sb[i] = *p++;
     typename IP::Lin L; double ws[IP::WS];
     L.ws = ws; L.g = 0; L.gmask = 0u;
-    IP::linearize(z, th, L);
-    IP::sensitivities(L, z, th, dq1, dq2, du);
+    double trc[IP::NTC1], trv[IP::NTV1];
+    M::trig_const(th, trc); M::trig_var(z.q, th, trv);
+    IP::linearize(z, th, trc, trv, L);
+    IP::sensitivities(L, z, th, trc, trv, dq1, dq2, du);
 }
 extern "C" int hc_contact_sens(int model, const double* z, const double* th, double* dq1, double* dq2, double* du) {
     switch (model) {
@@ -130,7 +134,9 @@ template <class M> static void K_t(const double* zz, const double* th, double* K
     for (int i = 0; i < M::NB; ++i) z.sb[i] = *p++;
     typename IP::Lin L; double ws[IP::WS];
     L.ws = ws; L.g = 0; L.gmask = 0u;
-    IP::assemble(z, th, L);
+    double trc[IP::NTC1], trv[IP::NTV1];
+    M::trig_const(th, trc); M::trig_var(z.q, th, trv);
+    IP::assemble(z, th, trc, trv, L);
     for (int i = 0; i < IP::NR; ++i) for (int j = 0; j < IP::NR; ++j) Kout[i * IP::NR + j] = L.K(i, j);
 }
 extern "C" int hc_contact_K(int model, const double* z, const double* th, double* K) {

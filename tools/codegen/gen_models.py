@@ -280,29 +280,81 @@ def model_planar_push():
                 d=d, phi=[phi], psit=psit, vT=vT)
 
 
+def hoist_trig(expr_lists, qsyms):
+    """Replace every sin(a)/cos(a) in the given expression lists by symbols.  Returns (new lists, const args, var args) where
+    `const` arguments depend on θ only (evaluated once per problem) and `var` arguments depend on q (once per candidate point).
+    Symbol for argument k of a class: <cls>S<k> / <cls>C<k>, stored in the array tr<cls>[2k], tr<cls>[2k+1]."""
+    args = []
+    for lst in expr_lists:
+        for e in lst:
+            for a in sp.sympify(e).atoms(sp.sin, sp.cos):
+                if a.args[0] not in args:
+                    args.append(a.args[0])
+    args = sorted(args, key=lambda a: sp.default_sort_key(a))
+    const = [a for a in args if not (a.free_symbols & set(qsyms))]
+    var = [a for a in args if a.free_symbols & set(qsyms)]
+    table = {}
+    syms = {"c": [], "v": []}
+    for cls, lst in (("c", const), ("v", var)):
+        for k, a in enumerate(lst):
+            S, Cc = sp.Symbol("tr%s%d" % (cls, 2 * k), real=True), sp.Symbol("tr%s%d" % (cls, 2 * k + 1), real=True)
+            table[sp.sin(a)] = S
+            table[sp.cos(a)] = Cc
+            syms[cls] += [S, Cc]
+    new_lists = [[sp.sympify(e).xreplace(table) for e in lst] for lst in expr_lists]
+    return new_lists, const, var, syms
+
+
+def emit_trig(fname, inputs, args, arr):
+    lines = ["__host__ __device__ __forceinline__ void %s(%s, double* __restrict__ %s) {" % (
+        fname, ", ".join("const double* __restrict__ %s" % n for n, _ in inputs), arr)]
+    used = set()
+    for a in args:
+        used |= a.free_symbols
+    for aname, syms in inputs:
+        for i, sy in enumerate(syms):
+            if sy in used:
+                lines.append("    const double %s = %s[%d];" % (sy.name, aname, i))
+    for k, a in enumerate(args):
+        lines.append("    sincos(%s, &%s[%d], &%s[%d]);" % (PR.doprint(a), arr, 2 * k, arr, 2 * k + 1))
+    if not args:
+        lines.append("    (void)%s;" % arr)
+    lines.append("}")
+    return "\n".join(lines) + "\n"
+
+
 def gen_contact(m):
     NQ, NU, NC, NP, NB = m["NQ"], m["NU"], m["NC"], m["NP"], m["NB"]
     q, gam, b, th = m["q"], m["gam"], m["b"], m["th"]
     thp = th[0:2 * NQ + NU]
-    ins = [("q", q), ("gam", gam), ("b", b), ("th", th)]
     d, phi, psit, vT = sp.Matrix(m["d"]), sp.Matrix(m["phi"]), sp.Matrix(m["psit"]), sp.Matrix(m["vT"])
 
     def J(f, x, n):
         return list(f.jacobian(sp.Matrix(x[:n]))) if (len(f) and n) else []
 
+    groups = [list(d), list(phi), list(psit), list(vT),
+              J(d, q, NQ), J(d, gam, NC), J(d, b, NB), J(phi, q, NQ), J(vT, q, NQ), J(psit, gam, NC),
+              J(d, thp, len(thp)), J(vT, thp, len(thp))]
+    groups, targs_c, targs_v, tsyms = hoist_trig(groups, q)
+    NTC, NTV = 2 * len(targs_c), 2 * len(targs_v)
+    ins = [("q", q), ("gam", gam), ("b", b), ("th", th), ("trc", tsyms["c"]), ("trv", tsyms["v"])]
+
     out = ["// GENERATED by tools/codegen/gen_models.py — do not edit.  Model: %s" % m["name"],
            "// Block-form residual pieces of the contact-implicit step (see csrc/contact_ip.cuh for the layout).",
+           "// sin/cos are hoisted: trig_const(θ) once per problem, trig_var(q,θ) once per candidate point; eq/jac/jacth take the tables.",
            "#pragma once", "namespace od { namespace gen_%s {" % m["name"],
-           "constexpr int NQ = %d, NU = %d, NC = %d, NP = %d, NB = %d, NTH = %d;" % (NQ, NU, NC, NP, NB, m["NTH"]), ""]
+           "constexpr int NQ = %d, NU = %d, NC = %d, NP = %d, NB = %d, NTH = %d, NTC = %d, NTV = %d;" % (NQ, NU, NC, NP, NB, m["NTH"], NTC, NTV), ""]
+    out.append(emit_trig("trig_const", [("th", th)], targs_c, "trc"))
+    out.append(emit_trig("trig_var", [("q", q), ("th", th)], targs_v, "trv"))
     total = {}
-    src, total["eq"] = emit_function("eq", ins, [("d", d), ("phi", phi), ("psit", psit), ("vT", vT)],
+    src, total["eq"] = emit_function("eq", ins, [("d", groups[0]), ("phi", groups[1]), ("psit", groups[2]), ("vT", groups[3])],
                                      "d(q,γ,b;θ), ϕ(q), ψ̂(γ;θ), vT(q;θ)")
     out.append(src)
-    src, total["jac"] = emit_function("jac", ins, [("D", J(d, q, NQ)), ("Eg", J(d, gam, NC)), ("Eb", J(d, b, NB)), ("N", J(phi, q, NQ)),
-                                                   ("V", J(vT, q, NQ)), ("Mpsi", J(psit, gam, NC))],
+    src, total["jac"] = emit_function("jac", ins, [("D", groups[4]), ("Eg", groups[5]), ("Eb", groups[6]), ("N", groups[7]),
+                                                   ("V", groups[8]), ("Mpsi", groups[9])],
                                       "row-major D[NQ×NQ], Eg[NQ×NC], Eb[NQ×NB], N[NC×NQ], V[NB×NQ], Mpsi[NP×NC]")
     out.append(src)
-    src, total["jacth"] = emit_function("jacth", ins, [("Dth", J(d, thp, len(thp))), ("Vth", J(vT, thp, len(thp)))],
+    src, total["jacth"] = emit_function("jacth", ins, [("Dth", groups[10]), ("Vth", groups[11])],
                                         "row-major Dth[NQ×(2NQ+NU)], Vth[NB×(2NQ+NU)]  (θ' = q1,q2,u)")
     out.append(src)
     out.append("constexpr int OPS_EQ = %d, OPS_JAC = %d, OPS_JACTH = %d;" % (total["eq"], total["jac"], total["jacth"]))
