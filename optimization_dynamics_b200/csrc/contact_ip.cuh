@@ -21,10 +21,13 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include "group_gj.cuh"
 
 // Every solver routine is __host__ __device__ so that tests/host_check.cu can single-step the very same template code on the
 // CPU against the oracle (a debugging aid for a GPU-less build container; liboptdyn_b200.so exports no host compute path).
+#ifndef OD_HD
 #define OD_HD __host__ __device__ __forceinline__
+#endif
 
 namespace od {
 
@@ -76,7 +79,11 @@ template <int N> struct cmax1 { static constexpr int v = N > 0 ? N : 1; };
 // configuration for small batches, where 4096 problems would otherwise occupy one warp per SM).  All lanes of a group hold
 // identical replicated state (z, r, direction) and evaluate the model redundantly; only the O(n³) factorisation is split by rows.
 // PPB = problems per block; the per-problem workspace is lane-interleaved in shared memory: element e of problem p at ws[e·PPB + p].
-template <class M, int G = 1, int PPB = 1>
+//
+// REG = true selects the register-resident linear algebra (group_gj.cuh): the reduced matrix is assembled through a small
+// shared-memory staging area (written redundantly by the lanes, read back one row set per lane), then factorised, and both Newton
+// right-hand sides solved, entirely in registers with warp shuffles.  Its workspace is contiguous per problem (ws[e]).
+template <class M, int G = 1, int PPB = 1, bool REG = false>
 struct ContactIP {
     static constexpr int NQ = M::NQ, NU = M::NU, NC = M::NC, NP = M::NP, NB = M::NB, NTH = M::NTH;
     static constexpr int NC1 = cmax1<NC>::v, NP1 = cmax1<NP>::v, NB1 = cmax1<NB>::v;
@@ -90,7 +97,21 @@ struct ContactIP {
     static constexpr int OFF_CP = OFF_PIV + NR;          // column permutation of the rank-revealing factorisation (robust IFT only)
     static constexpr int NZ = NQ + 2 * NC + 2 * NP + 2 * NB;
     static constexpr int OFF_ZS = OFF_CP + (M::ROBUST_IFT ? NR : 0);   // snapshot of the iterate at which the IFT is taken
-    static constexpr int WS = OFF_ZS + NZ;               // workspace doubles per problem
+    // REG workspace (contiguous per problem): staging rows [NR][PW] (K | carried right-hand sides; reused for the packed output
+    // row), iterate snapshot, q3.  Even pitch and offsets: rows are moved as 16-byte pairs; WS/2 odd spreads problems over banks.
+    static constexpr int PW = ((NR + NTP + 1) / 2) * 2;
+    static constexpr int ROFF_ZS = NR * PW;
+    static constexpr int ROFF_Q3 = ROFF_ZS + NZ;
+    static constexpr int RWS0 = ((ROFF_Q3 + NQ + 1) / 2) * 2;
+    static constexpr int RWS = ((RWS0 / 2) % 2 == 1) ? RWS0 : RWS0 + 2;
+    static constexpr int NOUT = NQ + NQ * NTP;           // packed output row [q3 | ∂q3/∂q1 | ∂q3/∂q2 | ∂q3/∂u1]
+    static_assert(!REG || NOUT <= NR * PW, "output row is staged in the matrix area");
+    static constexpr int WS = REG ? RWS : OFF_ZS + NZ;   // workspace doubles per problem
+    static constexpr int WS_STRIDE = REG ? 1 : PPB;      // distance between consecutive elements of one problem
+    static constexpr int WS_SLOT = REG ? RWS : 1;        // distance between the workspaces of consecutive problems of a block
+    typedef GroupGJ<NR, NR + 1, G> GJ;                   // Newton systems: one carried right-hand side (the affine one)
+    typedef GroupGJ<NR, NR + NTP, G> GJS;                // sensitivity system: all NTP right-hand sides carried
+    static constexpr int RPL = GJ::RPL;
 
     struct Z { double q[NQ], gam[NC1], s[NC1], psi[NP1], b[NB1], spsi[NP1], sb[NB1]; };
     // residual in block form; bilinear rows are stored at κ = 0 (r(z;κ) only shifts rgam and rc0 by −κ)
@@ -101,6 +122,9 @@ struct ContactIP {
         int g;                       // lane within the group
         unsigned gmask;              // __syncwarp mask of the group
         bool ok;
+        double a[REG ? RPL : 1][REG ? NR + 1 : 1];   // REG: this lane's rows of the eliminated [K | affine rhs]
+        int piv[REG ? NR : 1];                       // REG: pivot row of every elimination step
+        OD_HD double& S(int r, int j) const { return ws[r * PW + j]; }     // REG staging area
         OD_HD double& K(int i, int j) const { return ws[(i * NRP + j) * PPB]; }
         OD_HD double& X(int v, int i) const { return ws[(OFF_X + v * NRP + i) * PPB]; }
         OD_HD double& PIV(int i) const { return ws[(OFF_PIV + i) * PPB]; }
@@ -150,14 +174,99 @@ struct ContactIP {
     //   d_i  : D Δq + Eγ Δγ + Eb Δb                                              = rd
     //   γ_i  : γ_i N_i Δq + s_i Δγ_i                                             = rgam_i − γ_i rs_i
     //   c0_k : (Σ_j b_j V_j) Δq + sψ_k Mψ_k Δγ + Σ_j sb_j Δb_j + ψ_k Δsψ_k        = rc0_k − sψ_k rpsi_k + Σ_j b_j rv_j
-
-    // ---- linearise at z: model blocks → reduced matrix K → LU with partial pivoting (in the workspace) -----------------
-    //   unknowns x = [Δq | Δγ | Δb | Δsψ];  rows:
-    //   d_i  : D Δq + Eγ Δγ + Eb Δb                                              = rd
-    //   γ_i  : γ_i N_i Δq + s_i Δγ_i                                             = rgam_i − γ_i rs_i
-    //   c0_k : (Σ_j b_j V_j) Δq + sψ_k Mψ_k Δγ + Σ_j sb_j Δb_j + ψ_k Δsψ_k        = rc0_k − sψ_k rpsi_k + Σ_j b_j rv_j
     //   c1_j : ψ_k V_j Δq + sb_j Mψ_k Δγ + sψ_k Δb_j + b_j Δsψ_k                  = rc1_j − sb_j rpsi_k + ψ_k rv_j
-    OD_HD static void linearize(const Z& z, const double* th, const double* trc, const double* trv, Lin& L) { assemble(z, th, trc, trv, L); factor(L); }
+    // `r` is the residual at z: the REG path carries its reduced right-hand side (the affine Newton system) through the elimination.
+    OD_HD static void linearize(const Z& z, const double* th, const double* trc, const double* trv, const R& r, Lin& L) {
+        if constexpr (REG) {
+            double x[NR];
+            load_rhs(z, r, x);
+            stage_matrix(z, th, trc, trv, L);
+#pragma unroll
+            for (int i = 0; i < NR; ++i) L.S(i, NR) = x[i];
+            L.sync();
+            fetch_rows<NR + 1>(L, L.a);
+            L.ok = GJ::factor(L.a, L.piv, L.g, L.gmask);
+        } else {
+            assemble(z, th, trc, trv, L); factor(L);
+        }
+    }
+
+    // Row i of the reduced matrix (i is a compile-time constant wherever this is called from an unrolled loop).
+    OD_HD static void krow(const int i, const Z& z, const double* D, const double* Eg, const double* Eb, const Lin& L, double* row) {
+        if (i < NQ) {
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) row[j] = D[i * NQ + j];
+#pragma unroll
+            for (int j = 0; j < NC; ++j) row[NQ + j] = Eg[i * NC1 + j];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) row[NQ + NC + j] = Eb[i * NB1 + j];
+#pragma unroll
+            for (int j = 0; j < NP; ++j) row[NQ + NC + NB + j] = 0.0;
+        } else if (i < NQ + NC) {
+            const int c = (i - NQ < NC1) ? i - NQ : 0;
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) row[j] = z.gam[c] * L.N[c * NQ + j];
+#pragma unroll
+            for (int j = NQ; j < NR; ++j) row[j] = (j == i) ? z.s[c] : 0.0;
+        } else if (i < NQ + NC + NP) {
+            const int k = (i - NQ - NC < NP1) ? i - NQ - NC : 0;
+#pragma unroll
+            for (int c = 0; c < NQ; ++c) {
+                double acc = 0.0;
+#pragma unroll
+                for (int e = 0; e < M::cone_dim(k); ++e) acc += z.b[M::cone_off(k) + e] * L.V[(M::cone_off(k) + e) * NQ + c];
+                row[c] = acc;
+            }
+#pragma unroll
+            for (int c = 0; c < NC; ++c) row[NQ + c] = z.spsi[k] * L.Mpsi[k * NC1 + c];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) row[NQ + NC + j] = (cone_of(j) == k) ? z.sb[j] : 0.0;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) row[NQ + NC + NB + j] = (j == k) ? z.psi[k] : 0.0;
+        } else {
+            const int j = (i - NQ - NC - NP < NB1) ? i - NQ - NC - NP : 0;
+            const int k = cone_of(j);
+#pragma unroll
+            for (int c = 0; c < NQ; ++c) row[c] = z.psi[k] * L.V[j * NQ + c];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) row[NQ + c] = z.sb[j] * L.Mpsi[k * NC1 + c];
+#pragma unroll
+            for (int jj = 0; jj < NB; ++jj) row[NQ + NC + jj] = (jj == j) ? z.spsi[k] : 0.0;
+#pragma unroll
+            for (int kk = 0; kk < NP; ++kk) row[NQ + NC + NB + kk] = (kk == k) ? z.b[j] : 0.0;
+        }
+    }
+
+    // REG: model blocks → K rows into the staging area.  Every lane writes the same values (16-byte stores); the caller adds the
+    // right-hand-side columns and synchronises before fetch_rows.
+    OD_HD static void stage_matrix(const Z& z, const double* th, const double* trc, const double* trv, Lin& L) {
+        double D[NQ * NQ], Eg[NQ * NC1], Eb[NQ * NB1];
+        M::jac(z.q, z.gam, z.b, th, trc, trv, D, Eg, Eb, L.N, L.V, L.Mpsi);
+        L.sync();                                             // no lane may still be reading the staging area
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            double row[NR + 1];
+            krow(i, z, D, Eg, Eb, L, row);
+            double2* dst = reinterpret_cast<double2*>(&L.S(i, 0));
+#pragma unroll
+            for (int jj = 0; jj < NR / 2; ++jj) dst[jj] = make_double2(row[2 * jj], row[2 * jj + 1]);
+            if (NR % 2) L.S(i, NR - 1) = row[NR - 1];
+        }
+    }
+
+    // REG: this lane's rows r = s·G + g (first NCOLS columns) from the staging area into registers; padding rows are zero.
+    template <int NCOLS, int RA>
+    OD_HD static void fetch_rows(const Lin& L, double (&a)[RA][NCOLS]) {
+#pragma unroll
+        for (int s = 0; s < RPL; ++s) {
+            const int r = s * G + L.g;
+            const bool live = (G == 1) || ((s + 1) * G <= NR) || (r < NR);
+            const double2* src = reinterpret_cast<const double2*>(&L.S(live ? r : 0, 0));
+#pragma unroll
+            for (int jj = 0; jj < NCOLS / 2; ++jj) { const double2 v = src[jj]; a[s][2 * jj] = live ? v.x : 0.0; a[s][2 * jj + 1] = live ? v.y : 0.0; }
+            if (NCOLS % 2) { const double v = L.S(live ? r : 0, NCOLS - 1); a[s][NCOLS - 1] = live ? v : 0.0; }
+        }
+    }
     // every lane of the group writes the same values (benign); factor() synchronises before reading
     OD_HD static void assemble(const Z& z, const double* th, const double* trc, const double* trv, Lin& L) {
         static_assert(NTP >= G, "each lane needs a private scratch vector");
@@ -310,7 +419,27 @@ struct ContactIP {
     OD_HD static void solve(const Lin& L, const Z& z, const R& r, Z& D) {
         double x[NR];
         load_rhs(z, r, x);
-        lu_solve(L, x, &L.X(L.g, 0));
+        if constexpr (REG) {
+            double xm[RPL];
+            GJ::mine(x, xm, L.g);
+            GJ::solve(L.a, L.piv, xm, x, L.g, L.gmask);
+        } else {
+            lu_solve(L, x, &L.X(L.g, 0));
+        }
+        expand(L, r, x, D);
+    }
+    // REG: direction for the right-hand side that linearize() carried through the elimination (the residual at z itself)
+    OD_HD static void solve_carried(const Lin& L, const Z& z, const R& r, Z& D) {
+        if constexpr (REG) {
+            double x[NR];
+            GJ::extract(L.a, L.piv, 0, x, L.gmask);
+            expand(L, r, x, D);
+        } else {
+            solve(L, z, r, D);
+        }
+    }
+    // reduced solution x = (Δq, Δγ, Δb, Δsψ) → full direction
+    OD_HD static void expand(const Lin& L, const R& r, const double* x, Z& D) {
 #pragma unroll
         for (int i = 0; i < NQ; ++i) D.q[i] = x[i];
 #pragma unroll
@@ -343,7 +472,6 @@ struct ContactIP {
         }
     }
 
-    // ---- cone utilities --------------------------------------------------------------------------------------------
     // ---- cone utilities --------------------------------------------------------------------------------------------
     OD_HD static double step_length(const Z& z, const Z& D, double tau) {
         double bn = 1.0, bd = 1.0;                            // α = min(1, candidates)
@@ -392,7 +520,7 @@ struct ContactIP {
     // Newton direction at z (predictor, centering, Mehrotra corrector) and the step length along it
     OD_HD static void direction(const Lin& L, const Z& z, const R& r, double r_vio, double k_vio, Z& D, double& alpha) {
         if (NCONE > 0) {
-            solve(L, z, r, D);                                   // affine direction
+            solve_carried(L, z, r, D);                           // affine direction
             const double a_aff = step_length(z, D, 1.0);
             const double mu = cone_dot(z, D, 0.0) * (1.0 / (NCONE > 0 ? NCONE : 1));
             const double mu_aff = cone_dot(z, D, a_aff) * (1.0 / (NCONE > 0 ? NCONE : 1));
@@ -417,7 +545,7 @@ struct ContactIP {
             const double viol = fmax(r_vio, k_vio);
             alpha = step_length(z, D, fmax(0.95, 1.0 - viol * viol));
         } else {
-            solve(L, z, r, D);                                   // no cones: plain Newton direction, full step
+            solve_carried(L, z, r, D);                           // no cones: plain Newton direction, full step
             alpha = 1.0;
         }
     }
@@ -461,6 +589,51 @@ struct ContactIP {
             for (int i = 0; i < NQ; ++i) dst[i] = -x[i];
         }
         L.sync();
+    }
+
+    // REG variant: [K | NTP reduced right-hand sides] is staged once, every lane takes its rows (NR + NTP columns) into registers and
+    // one Gauss–Jordan pass leaves, in the pivot row of unknown i, the solution component i of every right-hand side.  The q rows
+    // are written (negated) into the packed output row in the staging area: OUT[NQ + c·NQ + i] = ∂q3_i/∂θ'_c.  Returns factor's ok.
+    OD_HD static bool sensitivities_reg(Lin& L, const Z& z, const double* th, const double* trc, const double* trv) {
+        stage_matrix(z, th, trc, trv, L);
+        {
+            double Dth[NQ * NTP], Vth[NB1 * NTP];
+            M::jacth(z.q, z.gam, z.b, th, trc, trv, Dth, Vth);
+            R r;
+#pragma unroll
+            for (int i = 0; i < NC1; ++i) { r.rs[i] = 0.0; r.rgam[i] = 0.0; }
+#pragma unroll
+            for (int i = 0; i < NP1; ++i) { r.rpsi[i] = 0.0; r.rc0[i] = 0.0; }
+#pragma unroll
+            for (int i = 0; i < NB1; ++i) r.rc1[i] = 0.0;
+#pragma unroll
+            for (int c = 0; c < NTP; ++c) {
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) r.d[i] = Dth[i * NTP + c];
+#pragma unroll
+                for (int j = 0; j < NB; ++j) r.rv[j] = Vth[j * NTP + c];
+                double x[NR];
+                load_rhs(z, r, x);
+#pragma unroll
+                for (int i = 0; i < NR; ++i) L.S(i, NR + c) = x[i];
+            }
+        }
+        L.sync();
+        double a[RPL][NR + NTP];
+        int piv[NR];
+        fetch_rows<NR + NTP>(L, a);
+        const bool ok = GJS::factor(a, piv, L.g, L.gmask);
+        L.sync();                                             // every lane has its rows: the staging area becomes the output row
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            const int wl = piv[i] & (G - 1), ws = piv[i] >> Grp<G>::LG;
+            const double inv = GJS::pick(a, i, ws);
+            if (L.g == wl) {
+#pragma unroll
+                for (int c = 0; c < NTP; ++c) L.ws[NQ + c * NQ + i] = -(GJS::pick(a, NR + c, ws) * inv);
+            }
+        }
+        return ok;
     }
 
     // ---- robust IFT for models with redundant contact constraints (planar push: 4 corner contacts on a 3-DoF block) ---------
@@ -534,28 +707,30 @@ struct ContactIP {
 
     // iterate ↔ workspace snapshot (all lanes of a group write identical values)
     OD_HD static void store_z(const Lin& L, const Z& z) {
-        double* p = &L.ws[OFF_ZS * PPB];
+        constexpr int ST = WS_STRIDE;
+        double* p = &L.ws[(REG ? ROFF_ZS : OFF_ZS) * ST];
         int e = 0;
 #pragma unroll
-        for (int i = 0; i < NQ; ++i) p[(e++) * PPB] = z.q[i];
+        for (int i = 0; i < NQ; ++i) p[(e++) * ST] = z.q[i];
 #pragma unroll
-        for (int i = 0; i < NC; ++i) { p[(e++) * PPB] = z.gam[i]; p[(e++) * PPB] = z.s[i]; }
+        for (int i = 0; i < NC; ++i) { p[(e++) * ST] = z.gam[i]; p[(e++) * ST] = z.s[i]; }
 #pragma unroll
-        for (int i = 0; i < NP; ++i) { p[(e++) * PPB] = z.psi[i]; p[(e++) * PPB] = z.spsi[i]; }
+        for (int i = 0; i < NP; ++i) { p[(e++) * ST] = z.psi[i]; p[(e++) * ST] = z.spsi[i]; }
 #pragma unroll
-        for (int i = 0; i < NB; ++i) { p[(e++) * PPB] = z.b[i]; p[(e++) * PPB] = z.sb[i]; }
+        for (int i = 0; i < NB; ++i) { p[(e++) * ST] = z.b[i]; p[(e++) * ST] = z.sb[i]; }
     }
     OD_HD static void load_z(const Lin& L, Z& z) {
-        const double* p = &L.ws[OFF_ZS * PPB];
+        constexpr int ST = WS_STRIDE;
+        const double* p = &L.ws[(REG ? ROFF_ZS : OFF_ZS) * ST];
         int e = 0;
 #pragma unroll
-        for (int i = 0; i < NQ; ++i) z.q[i] = p[(e++) * PPB];
+        for (int i = 0; i < NQ; ++i) z.q[i] = p[(e++) * ST];
 #pragma unroll
-        for (int i = 0; i < NC; ++i) { z.gam[i] = p[(e++) * PPB]; z.s[i] = p[(e++) * PPB]; }
+        for (int i = 0; i < NC; ++i) { z.gam[i] = p[(e++) * ST]; z.s[i] = p[(e++) * ST]; }
 #pragma unroll
-        for (int i = 0; i < NP; ++i) { z.psi[i] = p[(e++) * PPB]; z.spsi[i] = p[(e++) * PPB]; }
+        for (int i = 0; i < NP; ++i) { z.psi[i] = p[(e++) * ST]; z.spsi[i] = p[(e++) * ST]; }
 #pragma unroll
-        for (int i = 0; i < NB; ++i) { z.b[i] = p[(e++) * PPB]; z.sb[i] = p[(e++) * PPB]; }
+        for (int i = 0; i < NB; ++i) { z.b[i] = p[(e++) * ST]; z.sb[i] = p[(e++) * ST]; }
     }
 
     // initialize_z! (reference src/models/planar_push/simulator.jl:52-60 and the same pattern in the other models)
@@ -614,9 +789,9 @@ struct StepArgs {
 // of the tighter one.  The IFT is taken at the first iterate meeting the gradient tolerance, q3 at the first meeting the eval one.
 // The loop is a small state machine with ONE call site each for the residual, the factorisation and the direction, so that the
 // instruction footprint stays small and lanes of a warp that are in different phases (line search / new iteration) share code.
-template <class M, int G, int PPB>
+template <class M, int G, int PPB, bool REG = false>
 OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const int g, const unsigned gmask) {
-    typedef ContactIP<M, G, PPB> IP;
+    typedef ContactIP<M, G, PPB, REG> IP;
     constexpr int NQ = M::NQ, NU = M::NU;
     double th[M::NTH];
     typename IP::Z z, D, zc;
@@ -673,7 +848,10 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
         const bool conv_g = rok && (k_vio < a.opts.kappa_grad_tol);
         if (!eval_done && (conv_e || capped || bad)) {
             eval_done = true; it_e = it; st_e = bad ? ST_FAIL : (conv_e ? ST_OK : ST_MAXIT);
-            if (a.q3 && g == 0) {
+            if constexpr (REG) {                                 // kept in the workspace; written out with the rest of the row
+#pragma unroll
+                for (int k = 0; k < NQ; ++k) ws[IP::ROFF_Q3 + k] = z.q[k];
+            } else if (a.q3 && g == 0) {
                 double* o = a.q3 + (size_t)i * a.out_stride_q3;
 #pragma unroll
                 for (int k = 0; k < NQ; ++k) o[k] = z.q[k];
@@ -684,37 +862,74 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
             IP::store_z(L, z);
         }
         if (bad || capped || (eval_done && grad_done)) break;
-        IP::linearize(z, th, trc, trv, L);                       // trv still belongs to z (the candidate that was just accepted)
+        IP::linearize(z, th, trc, trv, rc, L);                   // trv still belongs to z (the candidate that was just accepted)
         if (!L.ok) { if (!eval_done) { st_e = ST_FAIL; it_e = it; } if (!grad_done) { st_g = ST_FAIL; it_g = it; IP::store_z(L, z); grad_done = true; } break; }
         IP::direction(L, z, rc, r_vio, k_vio, D, alpha);
         ls = 0;
     }
     // ---- IFT at the snapshot.  It sits after the loop on purpose: the problems of a warp converge at different iterations, and a
     // sensitivity pass inside the loop would be executed once per distinct convergence iteration (up to 8× per warp).
-    if (a.want_grad && a.dq1) {
-        IP::load_z(L, z);
-        M::trig_var(z.q, th, trv);
-        double* o1 = a.dq1 + (size_t)i * a.out_stride_dq; double* o2 = a.dq2 + (size_t)i * a.out_stride_dq; double* o3 = a.du + (size_t)i * a.out_stride_du;
-        if (M::ROBUST_IFT) {
-            IP::assemble(z, th, trc, trv, L);
-            if (!IP::sensitivities_robust(L, z, th, trc, trv, o1, o2, o3)) st_g = ST_FAIL;
+    if constexpr (REG) {
+        const bool grad = a.want_grad && a.dq1;
+        if (grad) {
+            IP::load_z(L, z);
+            M::trig_var(z.q, th, trv);
+            if (!IP::sensitivities_reg(L, z, th, trc, trv)) st_g = ST_FAIL;
         } else {
-            IP::linearize(z, th, trc, trv, L);
-            if (!L.ok) st_g = ST_FAIL;
-            IP::sensitivities(L, z, th, trc, trv, o1, o2, o3);
+            L.sync();
         }
-    }
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) ws[k] = ws[IP::ROFF_Q3 + k];          // (garbage when the eval solve failed before converging: status says so)
+        L.sync();
+        // ---- the packed row [q3 | ∂q3/∂q1 | ∂q3/∂q2 | ∂q3/∂u1] leaves the workspace: consecutive lanes take consecutive elements
+        constexpr int NOUT = IP::NOUT, NQQ = NQ * NQ;
+        double* oq = a.q3 ? a.q3 + (size_t)i * a.out_stride_q3 : nullptr;
+        double* o1 = grad ? a.dq1 + (size_t)i * a.out_stride_dq - NQ : nullptr;
+        double* o2 = grad ? a.dq2 + (size_t)i * a.out_stride_dq - (NQ + NQQ) : nullptr;
+        double* o3 = grad ? a.du + (size_t)i * a.out_stride_du - (NQ + 2 * NQQ) : nullptr;
+#pragma unroll
+        for (int t = 0; t < (NOUT + G - 1) / G; ++t) {
+            const int e = g + G * t;
+            if (G == 1 || e < NOUT) {
+                double* dst = (e < NQ) ? oq : (e < NQ + NQQ) ? o1 : (e < NQ + 2 * NQQ) ? o2 : o3;
+                if (dst) {
+                    const double v = ws[e];
+                    dst[e] = v;
 #ifdef __CUDA_ARCH__
-    if (a.n_peers > 1) {
-        L.sync();                                              // every lane's share of the row has been written
-        const size_t off = (size_t)(a.gather_row0 + i) * a.gather_width;
-        const double* row = a.peer_out[a.self_rank] + off;
-        for (int k = g; k < a.gather_width; k += G) {
-            const double v = __ldcg(row + k);
-            for (int p = 0; p < a.n_peers; ++p) if (p != a.self_rank) a.peer_out[p][off + k] = v;
-        }
-    }
+                    if (a.n_peers > 1) {
+                        const size_t off = (size_t)(a.gather_row0 + i) * a.gather_width + e;
+                        for (int p = 0; p < a.n_peers; ++p) if (p != a.self_rank) a.peer_out[p][off] = v;
+                    }
 #endif
+                }
+            }
+        }
+    } else {
+        if (a.want_grad && a.dq1) {
+            IP::load_z(L, z);
+            M::trig_var(z.q, th, trv);
+            double* o1 = a.dq1 + (size_t)i * a.out_stride_dq; double* o2 = a.dq2 + (size_t)i * a.out_stride_dq; double* o3 = a.du + (size_t)i * a.out_stride_du;
+            if (M::ROBUST_IFT) {
+                IP::assemble(z, th, trc, trv, L);
+                if (!IP::sensitivities_robust(L, z, th, trc, trv, o1, o2, o3)) st_g = ST_FAIL;
+            } else {
+                IP::assemble(z, th, trc, trv, L); IP::factor(L);
+                if (!L.ok) st_g = ST_FAIL;
+                IP::sensitivities(L, z, th, trc, trv, o1, o2, o3);
+            }
+        }
+#ifdef __CUDA_ARCH__
+        if (a.n_peers > 1) {
+            L.sync();                                              // every lane's share of the row has been written
+            const size_t off = (size_t)(a.gather_row0 + i) * a.gather_width;
+            const double* row = a.peer_out[a.self_rank] + off;
+            for (int k = g; k < a.gather_width; k += G) {
+                const double v = __ldcg(row + k);
+                for (int p = 0; p < a.n_peers; ++p) if (p != a.self_rank) a.peer_out[p][off + k] = v;
+            }
+        }
+#endif
+    }
     if (g == 0) {
         if (a.status) a.status[i] = st_e | (st_g << 4);
         if (a.iters) a.iters[i] = it_e | (it_g << 16);
@@ -722,14 +937,14 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
 }
 
 // BLOCK = G·PPB threads; dynamic shared memory = PPB × ContactIP::WS doubles.
-template <class M, int G, int PPB>
+template <class M, int G, int PPB, bool REG>
 __global__ void __launch_bounds__(G * PPB) contact_step_kernel(const StepArgs a) {
-    extern __shared__ double od_smem[];
+    extern __shared__ __align__(16) double od_smem[];
     const int slot = threadIdx.x / G, g = threadIdx.x % G;
     const int i = blockIdx.x * PPB + slot;
     if (i >= a.B) return;
     const unsigned gmask = (G >= 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) - g));
-    contact_step_one<M, G, PPB>(a, i, od_smem + slot, g, gmask);
+    contact_step_one<M, G, PPB, REG>(a, i, od_smem + slot * ContactIP<M, G, PPB, REG>::WS_SLOT, g, gmask);
 }
 
 }  // namespace od

@@ -163,35 +163,48 @@ int64_t od_launch_count(const od_handle* hd) { return hd ? hd->launches : 0; }
 
 }  // extern "C"
 
-template <class M, int G, int PPB>
+template <class M, int G, int PPB, bool REG>
 static cudaError_t launch_contact_cfg(const StepArgs& a, cudaStream_t s) {
     const int grid = (a.B + PPB - 1) / PPB;
-    constexpr size_t smem = sizeof(double) * PPB * ContactIP<M, G, PPB>::WS;
+    constexpr size_t smem = sizeof(double) * PPB * ContactIP<M, G, PPB, REG>::WS;
     if (smem > 48 * 1024) {   // > 48 KB of dynamic shared memory needs an explicit opt-in; per device, so set at every launch
-        cudaError_t e = cudaFuncSetAttribute(contact_step_kernel<M, G, PPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(contact_step_kernel<M, G, PPB, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    contact_step_kernel<M, G, PPB><<<grid, G * PPB, smem, s>>>(a);
+    contact_step_kernel<M, G, PPB, REG><<<grid, G * PPB, smem, s>>>(a);
     return cudaGetLastError();
 }
 
-// Lanes per problem: 1 = one thread per problem (throughput configuration, large batches); 4 / 8 = cooperative groups (latency
-// configuration: a 4096-problem batch alone would put a single warp on each SM).  OD_LANES overrides the heuristic.
+// Lanes per problem: 1 = one thread per problem (throughput configuration, large batches; LU in shared memory); 4 / 8 =
+// cooperative groups (latency configuration: a 4096-problem batch alone would put a single warp on each SM) with the
+// register-resident Gauss–Jordan of group_gj.cuh.  OD_LANES overrides the heuristic; OD_REG=0 forces the shared-memory LU.
 static int lanes_for(int B) {
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("OD_LANES"); forced = e ? atoi(e) : 0; }
     if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return forced;
-    if (B <= 32768) return 4;      // measured on B200 (hopper): 4096 problems 0.19 ms with 4 lanes vs 0.28 ms with 1; 262144: 1 lane wins
+    if (B <= 32768) return 4;
     return 1;
 }
+static bool reg_path() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("OD_REG"); v = e ? atoi(e) : 1; }
+    return v != 0;
+}
 
-template <class M, bool WIDE>
+// WIDE: models large enough for 8 lanes; REGOK: models whose IFT runs on the register path (not the rank-revealing one)
+template <class M, bool WIDE, bool REGOK>
 static cudaError_t launch_contact(const StepArgs& a, cudaStream_t s) {
     const int lanes = lanes_for(a.B);
-    if constexpr (WIDE) { if (lanes == 8) return launch_contact_cfg<M, 8, 4>(a, s); }
-    if (lanes >= 4) return launch_contact_cfg<M, 4, 8>(a, s);
-    if constexpr (WIDE) { if (lanes == 2) return launch_contact_cfg<M, 2, 16>(a, s); }
-    return launch_contact_cfg<M, 1, 32>(a, s);
+    if constexpr (REGOK) {
+        if (reg_path()) {
+            if constexpr (WIDE) { if (lanes == 8) return launch_contact_cfg<M, 8, 4, true>(a, s); }
+            if (lanes >= 4) return launch_contact_cfg<M, 4, 8, true>(a, s);
+        }
+    }
+    if constexpr (WIDE) { if (lanes == 8) return launch_contact_cfg<M, 8, 4, false>(a, s); }
+    if (lanes >= 4) return launch_contact_cfg<M, 4, 8, false>(a, s);
+    if constexpr (WIDE) { if (lanes == 2) return launch_contact_cfg<M, 2, 16, false>(a, s); }
+    return launch_contact_cfg<M, 1, 32, false>(a, s);
 }
 
 static int launch_step(od_handle* hd, StepArgs& a) {
@@ -202,12 +215,12 @@ static int launch_step(od_handle* hd, StepArgs& a) {
     a.opts.ls_scale = hd->opts.ls_scale; a.opts.max_iter = hd->opts.max_iter; a.opts.max_ls = hd->opts.max_ls;
     cudaError_t e;
     switch (hd->model) {
-        case OD_ACROBOT_IMPACT: e = launch_contact<AcrobotImpactModel, false>(a, hd->stream); break;
-        case OD_ACROBOT_NOMINAL: e = launch_contact<AcrobotNominalModel, false>(a, hd->stream); break;
-        case OD_CARTPOLE_FRICTION: e = launch_contact<CartpoleFrictionModel, false>(a, hd->stream); break;
-        case OD_CARTPOLE_FRICTIONLESS: e = launch_contact<CartpoleFrictionlessModel, false>(a, hd->stream); break;
-        case OD_PLANAR_PUSH: e = launch_contact<PlanarPushModel, true>(a, hd->stream); break;
-        case OD_HOPPER: e = launch_contact<HopperModel, true>(a, hd->stream); break;
+        case OD_ACROBOT_IMPACT: e = launch_contact<AcrobotImpactModel, false, true>(a, hd->stream); break;
+        case OD_ACROBOT_NOMINAL: e = launch_contact<AcrobotNominalModel, false, false>(a, hd->stream); break;
+        case OD_CARTPOLE_FRICTION: e = launch_contact<CartpoleFrictionModel, false, true>(a, hd->stream); break;
+        case OD_CARTPOLE_FRICTIONLESS: e = launch_contact<CartpoleFrictionlessModel, false, false>(a, hd->stream); break;
+        case OD_PLANAR_PUSH: e = launch_contact<PlanarPushModel, true, false>(a, hd->stream); break;
+        case OD_HOPPER: e = launch_contact<HopperModel, true, true>(a, hd->stream); break;
         default: return fail("this entry point needs a contact model handle (not OD_ROCKET)");
     }
     if (e != cudaSuccess) return fail("contact_step_kernel launch", e);

@@ -8,11 +8,19 @@
 
 using namespace od;
 
-template <class M> static void run_contact(const StepArgs& a) { double ws[ContactIP<M>::WS]; for (int i = 0; i < a.B; ++i) contact_step_one<M, 1, 1>(a, i, ws, 0, 0u); }
+template <class M> static void run_contact(const StepArgs& a, int reg) {
+    if (reg) {   // register-path algebra (group_gj.cuh) with one lane: shuffles are identities, the Gauss–Jordan arithmetic is the same
+        alignas(16) double ws[ContactIP<M, 1, 1, true>::WS];
+        for (int i = 0; i < a.B; ++i) contact_step_one<M, 1, 1, true>(a, i, ws, 0, 0u);
+    } else {
+        alignas(16) double ws[ContactIP<M>::WS];
+        for (int i = 0; i < a.B; ++i) contact_step_one<M, 1, 1>(a, i, ws, 0, 0u);
+    }
+}
 
 extern "C" int hc_contact_step(int model, int B, const double* q1, const double* q2, const double* u, int nq, int nu, double h, const double* fric,
                                double r_tol, double k_eval, double k_grad, int max_iter, int max_ls, int want_eval, int want_grad,
-                               const double* eta, int n_eta, double* q3, double* dq1, double* dq2, double* du, int* status, int* iters) {
+                               const double* eta, int n_eta, double* q3, double* dq1, double* dq2, double* du, int* status, int* iters, int reg) {
     StepArgs a; memset(&a, 0, sizeof(a));
     a.B = B; a.q1 = q1; a.q2 = q2; a.u = u; a.in_stride_q = nq; a.in_stride_u = nu;
     a.q3 = q3; a.dq1 = want_grad ? dq1 : nullptr; a.dq2 = dq2; a.du = du;
@@ -21,12 +29,12 @@ extern "C" int hc_contact_step(int model, int B, const double* q1, const double*
     for (int k = 0; k < 4; ++k) a.fric[k] = fric ? fric[k] : 0.0;
     a.opts.r_tol = r_tol; a.opts.kappa_eval_tol = k_eval; a.opts.kappa_grad_tol = k_grad; a.opts.ls_scale = 0.5; a.opts.max_iter = max_iter; a.opts.max_ls = max_ls;
     switch (model) {
-        case 0: run_contact<AcrobotImpactModel>(a); break;
-        case 1: run_contact<AcrobotNominalModel>(a); break;
-        case 2: run_contact<CartpoleFrictionModel>(a); break;
-        case 3: run_contact<CartpoleFrictionlessModel>(a); break;
-        case 4: run_contact<PlanarPushModel>(a); break;
-        case 5: run_contact<HopperModel>(a); break;
+        case 0: run_contact<AcrobotImpactModel>(a, reg); break;
+        case 1: run_contact<AcrobotNominalModel>(a, reg); break;
+        case 2: run_contact<CartpoleFrictionModel>(a, reg); break;
+        case 3: run_contact<CartpoleFrictionlessModel>(a, reg); break;
+        case 4: run_contact<PlanarPushModel>(a, reg && false); break;
+        case 5: run_contact<HopperModel>(a, reg); break;
         default: return 1;
     }
     return 0;
@@ -67,7 +75,7 @@ template <class M> static void resid_t(const double* zz, const double* th, doubl
     for (int i = 0; i < M::NB; ++i) *o++ = r.rc1[i];
     typename IP::Lin L; typename IP::Z D; double ws[IP::WS];
     L.ws = ws; L.g = 0; L.gmask = 0u;
-    IP::linearize(z, th, trc, trv, L);
+    IP::linearize(z, th, trc, trv, r, L);
     IP::solve(L, z, r, D);
     o = dir;
     for (int i = 0; i < M::NQ; ++i) *o++ = D.q[i];
@@ -107,7 +115,7 @@ template <class M> static void sens_t(const double* zz, const double* th, double
     L.ws = ws; L.g = 0; L.gmask = 0u;
     double trc[IP::NTC1], trv[IP::NTV1];
     M::trig_const(th, trc); M::trig_var(z.q, th, trv);
-    IP::linearize(z, th, trc, trv, L);
+    IP::assemble(z, th, trc, trv, L); IP::factor(L);
     IP::sensitivities(L, z, th, trc, trv, dq1, dq2, du);
 }
 extern "C" int hc_contact_sens(int model, const double* z, const double* th, double* dq1, double* dq2, double* du) {

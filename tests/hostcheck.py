@@ -35,7 +35,7 @@ def _p(a, t=C.c_double):
     return None if a is None else a.ctypes.data_as(C.POINTER(t))
 
 
-def step(model, q1, q2, u, h, k_eval=1e-4, k_grad=1e-3, fric=None, want_eval=True, want_grad=True, eta=None, r_tol=1e-8):
+def step(model, q1, q2, u, h, k_eval=1e-4, k_grad=1e-3, fric=None, want_eval=True, want_grad=True, eta=None, r_tol=1e-8, reg=False):
     nq, nu = DIMS[model]
     q1 = np.ascontiguousarray(q1, dtype=np.float64).reshape(-1, nq); B0 = q1.shape[0]
     q2 = np.ascontiguousarray(q2, dtype=np.float64).reshape(B0, nq)
@@ -53,7 +53,7 @@ def step(model, q1, q2, u, h, k_eval=1e-4, k_grad=1e-3, fric=None, want_eval=Tru
     q3 = np.zeros((B, nq)); dq1 = np.zeros((B, nq, nq)); dq2 = np.zeros((B, nq, nq)); du = np.zeros((B, nu, nq))
     st = np.zeros(B, dtype=np.int32); it = np.zeros(B, dtype=np.int32)
     rc = lib().hc_contact_step(MODELS[model], B, _p(q1), _p(q2), _p(u), nq, nu, C.c_double(h), _p(fr), C.c_double(r_tol), C.c_double(k_eval), C.c_double(k_grad),
-                               100, 25, int(want_eval), int(want_grad), _p(eta), n_eta, _p(q3), _p(dq1), _p(dq2), _p(du), _p(st, C.c_int), _p(it, C.c_int))
+                               100, 25, int(want_eval), int(want_grad), _p(eta), n_eta, _p(q3), _p(dq1), _p(dq2), _p(du), _p(st, C.c_int), _p(it, C.c_int), int(reg))
     assert rc == 0
     return dict(q3=q3, dq1=dq1, dq2=dq2, du=du, status=st, st_eval=st & 15, st_grad=(st >> 4) & 15, it_eval=it & 0xFFFF, it_grad=(it >> 16) & 0xFFFF)
 

@@ -16,13 +16,18 @@ from common import CONFIGS, compare, oracle_pair
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("name", list(CONFIGS))
-def test_solver_templates_match_oracle(name):
+REG_MODELS = ["hopper", "acrobot_impact", "cartpole_friction"]     # models whose latency configuration uses csrc/group_gj.cuh
+
+
+@pytest.mark.parametrize("name,reg", [(n, False) for n in CONFIGS] + [(n, True) for n in REG_MODELS])
+def test_solver_templates_match_oracle(name, reg):
+    """reg=False: shared-memory LU path (one thread per problem); reg=True: the register-resident Gauss–Jordan algebra of the
+    cooperative-lane path, run with one lane (shuffles are identities on the host)."""
     gen, h, ke, kg, fric, _ = CONFIGS[name]
     B = 1024 if name != "planar_push" else 512
     q1, q2, u = gen(B, h=h, seed=1)
     e, g = oracle_pair(O, name, q1, q2, u)
-    r = H.step(name, q1, q2, u, h, ke, kg, fric=fric)
+    r = H.step(name, q1, q2, u, h, ke, kg, fric=fric, reg=reg)
     tr = lambda a: a.transpose(0, 2, 1)
     eq, eg = compare(name, e, g, r["q3"], tr(r["dq1"]), tr(r["dq2"]), tr(r["du"]), r["st_eval"], r["st_grad"],
                      grad_outlier_fraction=0.0)
