@@ -120,7 +120,7 @@ struct ContactIP {
         double N[NC1 * NQ], V[NB1 * NQ], Mpsi[NP1 * NC1];
         double* ws;                  // workspace of this problem (already offset by the problem's slot)
         int g;                       // lane within the group
-        unsigned gmask;              // __syncwarp mask of the group
+        unsigned gmask;              // shuffle / __syncwarp mask (the whole warp: execution is warp-synchronous)
         bool ok;
         double a[REG ? RPL : 1][REG ? NR + 1 : 1];   // REG: this lane's rows of the eliminated [K | affine rhs]
         int piv[REG ? NR : 1];                       // REG: pivot row of every elimination step
@@ -789,6 +789,20 @@ struct StepArgs {
 // of the tighter one.  The IFT is taken at the first iterate meeting the gradient tolerance, q3 at the first meeting the eval one.
 // The loop is a small state machine with ONE call site each for the residual, the factorisation and the direction, so that the
 // instruction footprint stays small and lanes of a warp that are in different phases (line search / new iteration) share code.
+//
+// Warp-synchronous execution: every lane of a warp walks the state machine in lockstep until the slowest problem of the warp has
+// finished (finished problems keep executing with their state frozen; the padding lanes of a partial last warp repeat the last problem).
+// That costs nothing — a warp lasts as long as its slowest problem anyway — and makes every shuffle / __syncwarp a full-warp
+// operation on converged lanes: a partial-mask shuffle is bracketed by WARPSYNC/ENDCOLLECTIVE plus register moves (≈10 SASS
+// instructions per shuffle, measured), a full-mask one is a single SHFL.
+OD_HD bool warp_any(bool p) {
+#ifdef __CUDA_ARCH__
+    return __any_sync(0xffffffffu, p);
+#else
+    return p;
+#endif
+}
+
 template <class M, int G, int PPB, bool REG = false>
 OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const int g, const unsigned gmask) {
     typedef ContactIP<M, G, PPB, REG> IP;
@@ -826,6 +840,7 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
     double r_vio = 0.0, k_vio = 0.0, alpha = 0.0;
     D = z;                                  // any finite values: the first candidate uses alpha = 0
     bool first = true, eval_done = !a.want_eval, grad_done = !a.want_grad;
+    bool active = true;                    // this problem is still iterating
     int it = 0, ls = 0, it_e = 0, it_g = 0, st_e = 0, st_g = 0;
     for (;;) {
         // ---- candidate z − αΔ and its residual (the only residual call site) ----------------------------------------------
@@ -833,38 +848,45 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
         IP::candidate(z, D, alpha, zc);
         M::trig_var(zc.q, th, trv);
         IP::residual(zc, th, trc, trv, rc, rv2, kv2);
-        if (!(first || rv2 <= r_vio || kv2 <= k_vio || ls >= a.opts.max_ls)) {   // residual line search: halve and retry
-            alpha *= a.opts.ls_scale; ++ls;
-            continue;
-        }
-        z = zc; r_vio = rv2; k_vio = kv2;
-        if (!first) ++it;
-        first = false;
-        // ---- accepted iterate: termination tests ----------------------------------------------------------------------------
-        const bool bad = !IP::finite(z, r_vio, k_vio);
-        const bool capped = it >= a.opts.max_iter;
-        const bool rok = r_vio < a.opts.r_tol;
-        const bool conv_e = rok && (k_vio < a.opts.kappa_eval_tol);
-        const bool conv_g = rok && (k_vio < a.opts.kappa_grad_tol);
-        if (!eval_done && (conv_e || capped || bad)) {
-            eval_done = true; it_e = it; st_e = bad ? ST_FAIL : (conv_e ? ST_OK : ST_MAXIT);
-            if constexpr (REG) {                                 // kept in the workspace; written out with the rest of the row
+        const bool retry = active && !(first || rv2 <= r_vio || kv2 <= k_vio || ls >= a.opts.max_ls);
+        if (retry) { alpha *= a.opts.ls_scale; ++ls; }              // residual line search: halve and retry
+        if (warp_any(retry)) continue;                              // (the other problems of the warp re-evaluate their unchanged candidate)
+        if (active) {
+            z = zc; r_vio = rv2; k_vio = kv2;
+            if (!first) ++it;
+            first = false;
+            // ---- accepted iterate: termination tests ------------------------------------------------------------------------
+            const bool bad = !IP::finite(z, r_vio, k_vio);
+            const bool capped = it >= a.opts.max_iter;
+            const bool rok = r_vio < a.opts.r_tol;
+            const bool conv_e = rok && (k_vio < a.opts.kappa_eval_tol);
+            const bool conv_g = rok && (k_vio < a.opts.kappa_grad_tol);
+            if (!eval_done && (conv_e || capped || bad)) {
+                eval_done = true; it_e = it; st_e = bad ? ST_FAIL : (conv_e ? ST_OK : ST_MAXIT);
+                if constexpr (REG) {                             // kept in the workspace; written out with the rest of the row
 #pragma unroll
-                for (int k = 0; k < NQ; ++k) ws[IP::ROFF_Q3 + k] = z.q[k];
-            } else if (a.q3 && g == 0) {
-                double* o = a.q3 + (size_t)i * a.out_stride_q3;
+                    for (int k = 0; k < NQ; ++k) ws[IP::ROFF_Q3 + k] = z.q[k];
+                } else if (a.q3 && g == 0) {
+                    double* o = a.q3 + (size_t)i * a.out_stride_q3;
 #pragma unroll
-                for (int k = 0; k < NQ; ++k) o[k] = z.q[k];
+                    for (int k = 0; k < NQ; ++k) o[k] = z.q[k];
+                }
             }
+            if (!grad_done && (conv_g || capped || bad)) {       // the IFT itself is deferred until the loop has finished
+                grad_done = true; it_g = it; st_g = bad ? ST_FAIL : (conv_g ? ST_OK : ST_MAXIT);
+                IP::store_z(L, z);
+            }
+            if (bad || capped || (eval_done && grad_done)) active = false;
         }
-        if (!grad_done && (conv_g || capped || bad)) {           // the IFT itself is deferred until the loop has finished
-            grad_done = true; it_g = it; st_g = bad ? ST_FAIL : (conv_g ? ST_OK : ST_MAXIT);
-            IP::store_z(L, z);
-        }
-        if (bad || capped || (eval_done && grad_done)) break;
+        if (!warp_any(active)) break;
         IP::linearize(z, th, trc, trv, rc, L);                   // trv still belongs to z (the candidate that was just accepted)
-        if (!L.ok) { if (!eval_done) { st_e = ST_FAIL; it_e = it; } if (!grad_done) { st_g = ST_FAIL; it_g = it; IP::store_z(L, z); grad_done = true; } break; }
+        if (active && !L.ok) {
+            if (!eval_done) { st_e = ST_FAIL; it_e = it; eval_done = true; }
+            if (!grad_done) { st_g = ST_FAIL; it_g = it; IP::store_z(L, z); grad_done = true; }
+            active = false;
+        }
         IP::direction(L, z, rc, r_vio, k_vio, D, alpha);
+        if (!active) alpha = 0.0;                                // a finished problem stays where it is
         ls = 0;
     }
     // ---- IFT at the snapshot.  It sits after the loop on purpose: the problems of a warp converge at different iterations, and a
@@ -941,10 +963,10 @@ template <class M, int G, int PPB, bool REG>
 __global__ void __launch_bounds__(G * PPB) contact_step_kernel(const StepArgs a) {
     extern __shared__ __align__(16) double od_smem[];
     const int slot = threadIdx.x / G, g = threadIdx.x % G;
-    const int i = blockIdx.x * PPB + slot;
-    if (i >= a.B) return;
-    const unsigned gmask = (G >= 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) - g));
-    contact_step_one<M, G, PPB, REG>(a, i, od_smem + slot * ContactIP<M, G, PPB, REG>::WS_SLOT, g, gmask);
+    static_assert((G * PPB) % 32 == 0, "whole warps: the step runs warp-synchronously");
+    int i = blockIdx.x * PPB + slot;
+    if (i >= a.B) i = a.B - 1;               // padding lanes of the last warp repeat the last problem (identical values, same addresses)
+    contact_step_one<M, G, PPB, REG>(a, i, od_smem + slot * ContactIP<M, G, PPB, REG>::WS_SLOT, g, 0xffffffffu);
 }
 
 }  // namespace od
