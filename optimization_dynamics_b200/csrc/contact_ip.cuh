@@ -73,6 +73,16 @@ OD_HD void soc_step(double l0, const double* l1, double d0, const double* d1, do
     if (den > 0.0) frac_min(bn, bd, tau, den);
 }
 
+// Two-dimensional second-order cone (ψ; b), b scalar — every friction cone of the hopper and the cartpole: ψ ≥ |b| is the pair of
+// half-planes ψ − b ≥ 0, ψ + b ≥ 0, so the step to the boundary is the smaller of two orthant-type ratios.  In exact arithmetic
+// this equals the CVXOPT expression above (the eigenvalues of the scaled direction are the two ratios); it needs no division
+// and no square root.
+OD_HD void soc2_step(double l0, double l1, double d0, double d1, double tau, double& bn, double& bd) {
+    const double dm = d0 - d1, dp = d0 + d1;
+    if (dm > 0.0) frac_min(bn, bd, tau * (l0 - l1), dm);
+    if (dp > 0.0) frac_min(bn, bd, tau * (l0 + l1), dp);
+}
+
 template <int N> struct cmax1 { static constexpr int v = N > 0 ? N : 1; };
 
 // G lanes cooperate on one problem (G = 1: one thread per problem — the throughput configuration; G = 4/8: the latency
@@ -483,8 +493,8 @@ struct ContactIP {
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
             if (M::cone_dim(k) == 1) {
-                soc_step<1>(z.psi[k], &z.b[M::cone_off(k)], D.psi[k], &D.b[M::cone_off(k)], tau, bn, bd);
-                soc_step<1>(z.spsi[k], &z.sb[M::cone_off(k)], D.spsi[k], &D.sb[M::cone_off(k)], tau, bn, bd);
+                soc2_step(z.psi[k], z.b[M::cone_off(k)], D.psi[k], D.b[M::cone_off(k)], tau, bn, bd);
+                soc2_step(z.spsi[k], z.sb[M::cone_off(k)], D.spsi[k], D.sb[M::cone_off(k)], tau, bn, bd);
             } else {
                 soc_step<2>(z.psi[k], &z.b[M::cone_off(k)], D.psi[k], &D.b[M::cone_off(k)], tau, bn, bd);
                 soc_step<2>(z.spsi[k], &z.sb[M::cone_off(k)], D.spsi[k], &D.sb[M::cone_off(k)], tau, bn, bd);

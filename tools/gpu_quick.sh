@@ -3,7 +3,7 @@
 TAG=${1:-q}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q -s > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/${TAG}_pytest_gpu.log
-for CFG in "4 1" "8 1" "4 0" "1 0"; do
+for CFG in "4 1" "8 1" "16 1" "4 0" "1 0"; do
   set -- $CFG; L=$1; R=$2
   OD_LANES=$L OD_REG=$R timeout 300 python bench.py --no-cpu-baseline --extra --steps 100 > gpurun_out/${TAG}_bench_L${L}R${R}.json 2> gpurun_out/${TAG}_bench_L${L}R${R}.err
   python - <<PY
