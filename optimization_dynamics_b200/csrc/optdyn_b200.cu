@@ -276,20 +276,48 @@ int od_step_grad_packed_gather_device(od_handle* hd, int B, const double* in, lo
     return launch_step(hd, a);
 }
 
+// Device-visible alias of a pinned (page-locked, mapped) host buffer, or null for pageable memory (queried on every call: a
+// cached answer would go stale if the caller unpinned or freed the buffer).
+static void* mapped_alias(const void* host) {
+    if (!host) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged) return at.devicePointer;
+    return nullptr;
+}
+static int zero_copy_mode() {      // OD_ZEROCOPY: 0 = always stage through device buffers, 1 = outputs only, 2 = inputs and outputs (default)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("OD_ZEROCOPY"); v = e ? atoi(e) : 2; }
+    return v;
+}
+
+// Host-buffer entry point.  When the caller's buffers are pinned host memory (cudaHostAlloc / cudaHostRegister — what a Julia
+// or Python host uses for its trajectory arrays), the kernel reads the 80-B input rows and writes each finished 352-B output row
+// straight over PCIe: the device→host transfer of a row overlaps the problems that are still iterating, and the separate
+// cudaMemcpy calls (and their launch gaps) disappear.  Pageable buffers are staged through device memory as before.
 int od_step_grad_packed(od_handle* hd, int B, const double* in, double* out, int32_t* status) {
     if (!hd) return fail("null handle");
     Dims d; dims_of(hd->model, &d);
     if (hd->model == OD_ROCKET) return fail("od_step_grad_packed: use od_rocket_batch for OD_ROCKET");
     if (B <= 0) return 0;
+    if (!in || !out) return fail("od_step_grad_packed: null buffer");
     OD_CUDA(cudaSetDevice(hd->device));
     const size_t inw = 2 * d.nq + d.nu, outw = d.nq + d.nq * inw;
-    OD_CUDA(hd->in.reserve(sizeof(double) * inw * B));
-    OD_CUDA(hd->out.reserve(sizeof(double) * outw * B));
-    OD_CUDA(hd->st.reserve(sizeof(int32_t) * B));
-    OD_CUDA(cudaMemcpyAsync(hd->in.p, in, sizeof(double) * inw * B, cudaMemcpyHostToDevice, hd->stream));
-    if (od_step_grad_packed_device(hd, B, (const double*)hd->in.p, (double*)hd->out.p, (int32_t*)hd->st.p, nullptr, 1, 1)) return 1;
-    OD_CUDA(cudaMemcpyAsync(out, hd->out.p, sizeof(double) * outw * B, cudaMemcpyDeviceToHost, hd->stream));
-    if (status) OD_CUDA(cudaMemcpyAsync(status, hd->st.p, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, hd->stream));
+    const int zc = zero_copy_mode();
+    const double* din = zc >= 2 ? (const double*)mapped_alias(in) : nullptr;
+    double* dout = zc >= 1 ? (double*)mapped_alias(out) : nullptr;
+    int32_t* dst = (zc >= 1 && status) ? (int32_t*)mapped_alias(status) : nullptr;
+    if (!din) {
+        OD_CUDA(hd->in.reserve(sizeof(double) * inw * B));
+        OD_CUDA(cudaMemcpyAsync(hd->in.p, in, sizeof(double) * inw * B, cudaMemcpyHostToDevice, hd->stream));
+        din = (const double*)hd->in.p;
+    }
+    const bool stage_out = !dout, stage_st = !dst;
+    if (stage_out) { OD_CUDA(hd->out.reserve(sizeof(double) * outw * B)); dout = (double*)hd->out.p; }
+    if (stage_st) { OD_CUDA(hd->st.reserve(sizeof(int32_t) * B)); dst = (int32_t*)hd->st.p; }
+    if (od_step_grad_packed_device(hd, B, din, dout, dst, nullptr, 1, 1)) return 1;
+    if (stage_out) OD_CUDA(cudaMemcpyAsync(out, dout, sizeof(double) * outw * B, cudaMemcpyDeviceToHost, hd->stream));
+    if (stage_st && status) OD_CUDA(cudaMemcpyAsync(status, dst, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, hd->stream));
     OD_CUDA(cudaStreamSynchronize(hd->stream));
     return 0;
 }

@@ -81,6 +81,8 @@ class ImplicitDynamics:
         self._friction_seen = None
         self._hd = None
         self._make_handle()
+        self._packed_cache = None
+        self._lib = L
         self._memo_key = None      # (x, u) of the last gradient solve: fx and fu share one launch (reference solves twice)
         self._memo = None
 
@@ -95,11 +97,11 @@ class ImplicitDynamics:
         if self._hd:
             L.od_destroy(self._hd)
         self._hd = hd
-        self._friction_seen = None if fr is None else fr.copy()
+        self._friction_seen = None if fr is None else fr.tobytes()
 
     def _handle(self):
         fr = self.model.friction
-        if fr is not None and not np.array_equal(fr, self._friction_seen):
+        if fr is not None and fr.tobytes() != self._friction_seen:
             self._make_handle()
             self._memo_key = None
         return self._hd
@@ -137,10 +139,24 @@ class ImplicitDynamics:
         """Packed rows in [q1|q2|u] → out [q3 | ∂q3/∂q1 | ∂q3/∂q2 | ∂q3/∂u1] (blocks column-major).  Fewest transfers."""
         inw = 2 * self.nq + self.nu
         outw = self.nq + self.nq * inw
-        xin = _f64(xin, (-1, inw)); B = xin.shape[0]
-        out = np.empty((B, outw)) if out is None else out
-        status = np.empty(B, dtype=np.int32) if status is None else status
-        _lib.check(_lib.lib().od_step_grad_packed(self._handle(), B, _dp(xin), _dp(out), _ip(status)))
+        c = self._packed_cache          # repeated calls on the same buffers (a solver's trajectory arrays) skip the numpy→ctypes conversions
+        if c is not None and c[0] is xin and c[1] is out and c[2] is status:
+            B, pin, pout, pst = c[3:]
+        else:
+            keep = xin, out, status
+            xin = _f64(xin, (-1, inw)); B = xin.shape[0]
+            out = np.empty((B, outw)) if out is None else out
+            status = np.empty(B, dtype=np.int32) if status is None else status
+            if out.shape != (B, outw) or out.dtype != np.float64 or not out.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous float64 array of shape (%d, %d)" % (B, outw))
+            if status.shape != (B,) or status.dtype != np.int32:
+                raise ValueError("status must be an int32 array of shape (%d,)" % B)
+            pin, pout, pst = _dp(xin), _dp(out), _ip(status)
+            if keep[0] is xin and keep[1] is out and keep[2] is status:
+                self._packed_cache = (xin, out, status, B, pin, pout, pst)
+        rc = self._lib.od_step_grad_packed(self._handle(), B, pin, pout, pst)
+        if rc:
+            _lib.check(rc)
         return out, status
 
     def launch_count(self):
