@@ -53,6 +53,8 @@ def _ip(a):
 
 def _f64(a, shape):
     a = np.ascontiguousarray(a, dtype=np.float64)
+    if a.ndim == len(shape) and all(s == -1 or s == n for s, n in zip(shape, a.shape)):
+        return a                       # already the right shape: keep the caller's object (identity is used for call caching)
     return a.reshape(shape)
 
 
