@@ -334,11 +334,11 @@ def main():
                                       if fused is not None else "kernel + ncclAllGather of 352-B rows"),
                        "gather_check_bitwise_equal_to_nccl": gather_check, "converged_fraction": ok_frac},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
-                         "kernel": "od::contact_step_kernel<HopperModel,32>", "kernel_ms": ker_ms_per, "algorithmic_bytes_per_launch": (BYTES_IN + BYTES_OUT) * B,
+                         "kernel": "od::contact_step_kernel<HopperModel, lanes=%d, problems/block=%d, register Gauss-Jordan>" % ((8, 4) if B <= 8192 else (4, 8)), "kernel_ms": ker_ms_per, "algorithmic_bytes_per_launch": (BYTES_IN + BYTES_OUT) * B,
                          "peak_source": peak_src,
                          "note": "432 B vs ~1e5 fp64 flop per unit: the kernel is fp64-latency bound by construction (DESIGN.md §Roofline)"},
             "e2e": {"value": B_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": BYTES_IN * B, "d2h_bytes_per_step": (BYTES_OUT + 4) * B,
-                    "ms_per_step": 1e3 * e2e_s / args.steps, "api": "ImplicitDynamics.step_grad_packed -> od_step_grad_packed (pinned host buffers)"},
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "api": "ImplicitDynamics.step_grad_packed -> od_step_grad_packed (pinned host buffers: inputs copied H2D, output rows written by the kernel straight into host memory over PCIe)"},
             "gpu_launches": int(launches) * world,
             "clocks": clk,
             "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
