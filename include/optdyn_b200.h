@@ -91,6 +91,21 @@ int od_step_grad_packed_device(od_handle* hd, int B, const double* in, double* o
 int od_step_grad_packed_gather_device(od_handle* hd, int B, const double* in, long long row0, int world, int rank,
                                       const uint64_t* gather_buffers, int32_t* status, int32_t* iters);
 
+/* Batched closed-loop rollouts — the caller of f in the outer solver: iLQR.rollout(model, x1, ū) (reference examples/cartpole.jl:79,
+ * acrobot.jl:92, planar_push.jl:113, hopper.jl:272) and the forward pass / Armijo line search of IterativeLQR (step sizes down to
+ * 1e-5, examples/cartpole.jl:86).  R rollouts of T knot points in ONE launch; time is sequential inside the kernel:
+ *     u_t = ū_t + α_r k_t + K_t (x_t − x̄_t),     x_{t+1} = f(x_t, u_t) = [q2; q3]        (src/dynamics.jl:81-94)
+ * x1: R×2nq initial states [q1; q2].  ubar: (T−1)×nu shared by all rollouts (ubar_per_rollout = 0) or R×(T−1)×nu.
+ * xbar: T×2nq, K: (T−1)×nu×2nq row-major [t][control][state], kff: (T−1)×nu, alpha: R — each may be NULL (K needs xbar;
+ * alpha NULL = 1): all NULL is the open-loop rollout.  X: R×T×2nq, U: R×(T−1)×nu (U may be NULL in the host variant),
+ * status: R×(T−1) per-step solver status (0 = converged; may be NULL). */
+int od_rollout_batch(od_handle* hd, int R, int T, const double* x1, const double* ubar, int ubar_per_rollout, const double* xbar,
+                     const double* K, const double* kff, const double* alpha, double* X, double* U, int32_t* status);
+/* Device pointers, asynchronous; ubar_stride = doubles between the controls of consecutive rollouts (0 = shared). */
+int od_rollout_batch_device(od_handle* hd, int R, int T, const double* x1, const double* ubar, long long ubar_stride,
+                            const double* xbar, const double* K, const double* kff, const double* alpha, double* X, double* U,
+                            int32_t* status, int32_t* iters);
+
 /* Gradient bundle — gradient!(eval_sim, gb, q1, q2, u1), reference src/gradient_bundle.jl:87-104: one nominal and N perturbed
  * eval-sim steps per problem ((N+1)·B solves in one launch), then the least-squares fit of src/ls.jl:44-60 in closed form
  * (normal equations).  eta: N×(2nq+nu) perturbations shared by the batch (host).  dz: B×(nq×(2nq+nu)) column-major (host).

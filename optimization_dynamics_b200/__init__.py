@@ -6,9 +6,10 @@ from .dynamics import (ImplicitDynamics, Model, f, fx, fu, state_to_configuratio
 from .gradient_bundle import GradientBundle, gradient, gradient_batch, fx_gb, fu_gb
 from .rocket import (RocketInfo, f_rocket, fx_rocket, fu_rocket, soc_projection, soc_projection_gradient, f_rocket_proj, fx_rocket_proj,
                      fu_rocket_proj)
+from .rollout import rollout, rollout_batch
 from . import workloads
 
 __all__ = ["ImplicitDynamics", "Model", "f", "fx", "fu", "state_to_configuration", "GradientBundle", "gradient", "gradient_batch", "fx_gb",
            "fu_gb", "RocketInfo", "f_rocket", "fx_rocket", "fu_rocket", "soc_projection", "soc_projection_gradient", "f_rocket_proj",
            "fx_rocket_proj", "fu_rocket_proj", "acrobot_impact", "acrobot_nominal", "cartpole_friction", "cartpole_frictionless",
-           "planarpush", "hopper", "rocket", "workloads"]
+           "planarpush", "hopper", "rocket", "rollout", "rollout_batch", "workloads"]

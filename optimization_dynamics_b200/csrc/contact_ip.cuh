@@ -983,4 +983,80 @@ __global__ void __launch_bounds__(G * PPB) contact_step_kernel(const StepArgs a)
     contact_step_one<M, G, PPB, REG>(a, i, od_smem + slot * ContactIP<M, G, PPB, REG>::WS_SLOT, g, 0xffffffffu);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Batched closed-loop rollouts: the caller of f in the reference's outer solver — iLQR.rollout(model, x1, ū) and the forward
+// pass / Armijo line search of IterativeLQR (reference examples/cartpole.jl:79,86; the package itself is external).  Time is
+// sequential, rollouts (line-search candidates α_r, or independent rollouts) are parallel: ONE launch instead of T−1, the state
+// x_t = [q1; q2] never leaves the device.  Step t of rollout r:
+//     u_t = ū_t + α_r k_t + K_t (x_t − x̄_t)          (k, K, x̄ may be null: open-loop rollout)
+//     x_{t+1} = f(x_t, u_t) = [q2; q3],  q3 = step!(eval_sim, q2, (q2 − q1)/h, u_t)        reference src/dynamics.jl:81-94
+// X (R × T × 2NQ) and U (R × (T−1) × NU) are outputs and also the working storage: every step is the same contact_step_one as
+// the batched entry points, reading row t of X/U and writing q3 into row t+1.
+struct RolloutArgs {
+    int R, T;
+    const double* x1;                      // R × 2NQ
+    const double* ubar; long long ubar_stride;   // (T−1) × NU nominal controls; stride between rollouts in doubles (0 = shared)
+    const double* xbar;                    // T × 2NQ nominal states, or null
+    const double* K;                       // (T−1) × NU × 2NQ feedback gains, row-major [t][u component][x component], or null
+    const double* kff;                     // (T−1) × NU feed-forward terms, or null
+    const double* alpha;                   // R step sizes, or null (α = 1)
+    double* X; double* U;
+    int* status; int* iters;               // R × (T−1), may be null
+    double h; double fric[4];
+    SolverOpts opts;
+};
+
+template <class M, int G, int PPB, bool REG>
+OD_HD void contact_rollout_one(const RolloutArgs& ra, const int r, double* ws, const int g, const unsigned gmask) {
+    constexpr int NQ = M::NQ, NU = M::NU, NX = 2 * M::NQ;
+    const int T = ra.T;
+    double* Xr = ra.X + (size_t)r * T * NX;
+    double* Ur = ra.U + (size_t)r * (T - 1) * NU;
+    StepArgs a;
+    a.B = T - 1; a.q1 = Xr; a.q2 = Xr + NQ; a.u = Ur; a.in_stride_q = NX; a.in_stride_u = NU;
+    a.q3 = Xr + NX + NQ; a.dq1 = nullptr; a.dq2 = nullptr; a.du = nullptr;
+    a.out_stride_q3 = NX; a.out_stride_dq = 0; a.out_stride_du = 0;
+    a.status = ra.status ? ra.status + (size_t)r * (T - 1) : nullptr;
+    a.iters = ra.iters ? ra.iters + (size_t)r * (T - 1) : nullptr;
+    a.h = ra.h;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a.fric[k] = ra.fric[k];
+    a.want_eval = 1; a.want_grad = 0; a.eta = nullptr; a.n_eta = 0;
+    a.n_peers = 0; a.self_rank = 0; a.gather_row0 = 0; a.gather_width = 0;
+    a.opts = ra.opts;
+    const double alpha = ra.alpha ? ra.alpha[r] : 1.0;
+    const double* ub = ra.ubar + (size_t)r * ra.ubar_stride;
+    for (int e = g; e < NX; e += G) Xr[e] = ra.x1[(size_t)r * NX + e];
+    for (int t = 0; t < T - 1; ++t) {
+#ifdef __CUDA_ARCH__
+        __syncwarp(gmask);                                     // x_t (written by other lanes) is visible
+#endif
+        for (int e = g; e < NU; e += G) {
+            double u = ub[(size_t)t * NU + e];
+            if (ra.kff) u += alpha * ra.kff[(size_t)t * NU + e];
+            if (ra.K) {
+                const double* Kr = ra.K + ((size_t)t * NU + e) * NX;
+                double acc = 0.0;
+                for (int j = 0; j < NX; ++j) acc += Kr[j] * (Xr[(size_t)t * NX + j] - (ra.xbar ? ra.xbar[(size_t)t * NX + j] : 0.0));
+                u += acc;
+            }
+            Ur[(size_t)t * NU + e] = u;
+        }
+        for (int e = g; e < NQ; e += G) Xr[(size_t)(t + 1) * NX + e] = Xr[(size_t)t * NX + NQ + e];
+#ifdef __CUDA_ARCH__
+        __syncwarp(gmask);
+#endif
+        contact_step_one<M, G, PPB, REG>(a, t, ws, g, gmask);
+    }
+}
+
+template <class M, int G, int PPB, bool REG>
+__global__ void __launch_bounds__(G * PPB) contact_rollout_kernel(const RolloutArgs ra) {
+    extern __shared__ __align__(16) double od_smem[];
+    const int slot = threadIdx.x / G, g = threadIdx.x % G;
+    int r = blockIdx.x * PPB + slot;
+    if (r >= ra.R) r = ra.R - 1;             // padding lanes repeat the last rollout (identical values, same addresses)
+    contact_rollout_one<M, G, PPB, REG>(ra, r, od_smem + slot * ContactIP<M, G, PPB, REG>::WS_SLOT, g, 0xffffffffu);
+}
+
 }  // namespace od

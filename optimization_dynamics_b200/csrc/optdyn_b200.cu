@@ -208,6 +208,30 @@ static cudaError_t launch_contact(const StepArgs& a, cudaStream_t s) {
     return launch_contact_cfg<M, 1, 32, false>(a, s);
 }
 
+template <class M, int G, int PPB, bool REG>
+static cudaError_t launch_rollout_cfg(const RolloutArgs& a, cudaStream_t s) {
+    const int grid = (a.R + PPB - 1) / PPB;
+    constexpr size_t smem = sizeof(double) * PPB * ContactIP<M, G, PPB, REG>::WS;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(contact_rollout_kernel<M, G, PPB, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    contact_rollout_kernel<M, G, PPB, REG><<<grid, G * PPB, smem, s>>>(a);
+    return cudaGetLastError();
+}
+// rollouts are latency-bound for any realistic count (≤ a few thousand): cooperative lanes, register path where the model has it
+template <class M, bool WIDE, bool REGOK>
+static cudaError_t launch_rollout(const RolloutArgs& a, cudaStream_t s) {
+    const int lanes = lanes_for(a.R);
+    if constexpr (REGOK) {
+        if (reg_path()) {
+            if constexpr (WIDE) { if (lanes == 8) return launch_rollout_cfg<M, 8, 4, true>(a, s); }
+            return launch_rollout_cfg<M, 4, 8, true>(a, s);
+        }
+    }
+    return launch_rollout_cfg<M, 4, 8, false>(a, s);
+}
+
 static int launch_step(od_handle* hd, StepArgs& a) {
     if (a.B <= 0) return 0;
     a.h = hd->h;
@@ -366,6 +390,71 @@ int od_step_grad_batch(od_handle* hd, int B, const double* q1, const double* q2,
 int od_step_batch(od_handle* hd, int B, const double* q1, const double* q2, const double* u, double* q3, int32_t* status) {
     if (!q3) return fail("od_step_batch: q3 is null");
     return od_step_grad_batch(hd, B, q1, q2, u, q3, nullptr, nullptr, nullptr, status);
+}
+
+int od_rollout_batch_device(od_handle* hd, int R, int T, const double* x1, const double* ubar, long long ubar_stride, const double* xbar,
+                            const double* K, const double* kff, const double* alpha, double* X, double* U, int32_t* status, int32_t* iters) {
+    if (!hd) return fail("null handle");
+    if (hd->model == OD_ROCKET) return fail("od_rollout_batch: contact models only");
+    if (R <= 0 || T <= 1) return 0;
+    if (!x1 || !ubar || !X || !U) return fail("od_rollout_batch: x1, ubar, X and U are required");
+    if (K && !xbar) return fail("od_rollout_batch: feedback gains K need the nominal states xbar");
+    OD_CUDA(cudaSetDevice(hd->device));
+    RolloutArgs a; memset(&a, 0, sizeof(a));
+    a.R = R; a.T = T; a.x1 = x1; a.ubar = ubar; a.ubar_stride = ubar_stride; a.xbar = xbar; a.K = K; a.kff = kff; a.alpha = alpha;
+    a.X = X; a.U = U; a.status = status; a.iters = iters; a.h = hd->h;
+    for (int k = 0; k < 4; ++k) a.fric[k] = hd->params[k];
+    a.opts.r_tol = hd->opts.r_tol; a.opts.kappa_eval_tol = hd->opts.kappa_eval_tol; a.opts.kappa_grad_tol = hd->opts.kappa_grad_tol;
+    a.opts.ls_scale = hd->opts.ls_scale; a.opts.max_iter = hd->opts.max_iter; a.opts.max_ls = hd->opts.max_ls;
+    cudaError_t e;
+    switch (hd->model) {
+        case OD_ACROBOT_IMPACT: e = launch_rollout<AcrobotImpactModel, false, true>(a, hd->stream); break;
+        case OD_ACROBOT_NOMINAL: e = launch_rollout<AcrobotNominalModel, false, false>(a, hd->stream); break;
+        case OD_CARTPOLE_FRICTION: e = launch_rollout<CartpoleFrictionModel, false, true>(a, hd->stream); break;
+        case OD_CARTPOLE_FRICTIONLESS: e = launch_rollout<CartpoleFrictionlessModel, false, false>(a, hd->stream); break;
+        case OD_PLANAR_PUSH: e = launch_rollout<PlanarPushModel, true, false>(a, hd->stream); break;
+        case OD_HOPPER: e = launch_rollout<HopperModel, true, true>(a, hd->stream); break;
+        default: return fail("od_rollout_batch: bad model");
+    }
+    if (e != cudaSuccess) return fail("contact_rollout_kernel launch", e);
+    hd->launches++;
+    return 0;
+}
+
+int od_rollout_batch(od_handle* hd, int R, int T, const double* x1, const double* ubar, int ubar_per_rollout, const double* xbar,
+                     const double* K, const double* kff, const double* alpha, double* X, double* U, int32_t* status) {
+    if (!hd) return fail("null handle");
+    Dims d; dims_of(hd->model, &d);
+    if (hd->model == OD_ROCKET) return fail("od_rollout_batch: contact models only");
+    if (R <= 0 || T <= 1) return 0;
+    if (!x1 || !ubar || !X) return fail("od_rollout_batch: x1, ubar and X are required");
+    if (K && !xbar) return fail("od_rollout_batch: feedback gains K need the nominal states xbar");
+    OD_CUDA(cudaSetDevice(hd->device));
+    const size_t nx = 2 * d.nq, nu = d.nu, S = T - 1;
+    const size_t n_x1 = (size_t)R * nx, n_ub = (ubar_per_rollout ? (size_t)R : 1) * S * nu, n_xb = xbar ? (size_t)T * nx : 0;
+    const size_t n_K = K ? S * nu * nx : 0, n_k = kff ? S * nu : 0, n_al = alpha ? (size_t)R : 0;
+    const size_t n_in = n_x1 + n_ub + n_xb + n_K + n_k + n_al;
+    const size_t n_X = (size_t)R * T * nx, n_U = (size_t)R * S * nu;
+    OD_CUDA(hd->in.reserve(sizeof(double) * n_in));
+    OD_CUDA(hd->out.reserve(sizeof(double) * (n_X + n_U)));
+    OD_CUDA(hd->st.reserve(sizeof(int32_t) * (size_t)R * S));
+    double* p = (double*)hd->in.p;
+    double* d_x1 = p; p += n_x1; double* d_ub = p; p += n_ub;
+    double* d_xb = xbar ? p : nullptr; p += n_xb; double* d_K = K ? p : nullptr; p += n_K;
+    double* d_k = kff ? p : nullptr; p += n_k; double* d_al = alpha ? p : nullptr;
+    OD_CUDA(cudaMemcpyAsync(d_x1, x1, sizeof(double) * n_x1, cudaMemcpyHostToDevice, hd->stream));
+    OD_CUDA(cudaMemcpyAsync(d_ub, ubar, sizeof(double) * n_ub, cudaMemcpyHostToDevice, hd->stream));
+    if (xbar) OD_CUDA(cudaMemcpyAsync(d_xb, xbar, sizeof(double) * n_xb, cudaMemcpyHostToDevice, hd->stream));
+    if (K) OD_CUDA(cudaMemcpyAsync(d_K, K, sizeof(double) * n_K, cudaMemcpyHostToDevice, hd->stream));
+    if (kff) OD_CUDA(cudaMemcpyAsync(d_k, kff, sizeof(double) * n_k, cudaMemcpyHostToDevice, hd->stream));
+    if (alpha) OD_CUDA(cudaMemcpyAsync(d_al, alpha, sizeof(double) * n_al, cudaMemcpyHostToDevice, hd->stream));
+    double* d_X = (double*)hd->out.p; double* d_U = d_X + n_X;
+    if (od_rollout_batch_device(hd, R, T, d_x1, d_ub, ubar_per_rollout ? (long long)(S * nu) : 0, d_xb, d_K, d_k, d_al, d_X, d_U, (int32_t*)hd->st.p, nullptr)) return 1;
+    OD_CUDA(cudaMemcpyAsync(X, d_X, sizeof(double) * n_X, cudaMemcpyDeviceToHost, hd->stream));
+    if (U) OD_CUDA(cudaMemcpyAsync(U, d_U, sizeof(double) * n_U, cudaMemcpyDeviceToHost, hd->stream));
+    if (status) OD_CUDA(cudaMemcpyAsync(status, hd->st.p, sizeof(int32_t) * (size_t)R * S, cudaMemcpyDeviceToHost, hd->stream));
+    OD_CUDA(cudaStreamSynchronize(hd->stream));
+    return 0;
 }
 
 int od_bundle_batch(od_handle* hd, int B, int N, const double* eta, const double* q1, const double* q2, const double* u, double* dz, int32_t* status) {

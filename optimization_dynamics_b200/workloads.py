@@ -81,6 +81,32 @@ def rocket_batch(B, seed=0, u_max=12.5):
     return np.ascontiguousarray(x), np.ascontiguousarray(u)
 
 
+def hopper_rollout_inputs(R, T=21, h=0.05, seed=0):
+    """Forward-pass workload around the reference's hopper initial rollout (examples/hopper.jl:178,270-272): x1 = [q; q] with the
+    foot on the ground, stand controls ū, plus a seeded feedback policy (K, k) and R step sizes α = 1, ½, ¼, … ≥ 1e-5
+    (the Armijo candidates of examples/hopper.jl:276-278)."""
+    rng = np.random.default_rng(seed)
+    q = np.array([0.0, 0.5 + HOPPER["foot_radius"], 0.0, 0.5])
+    x1 = np.concatenate([q, q])
+    ubar = np.tile(np.array([0.0, HOPPER["gravity"] * HOPPER["mass_body"] * 0.5 * h]), (T - 1, 1)) + rng.normal(0.0, 0.05, (T - 1, 2))
+    k = rng.normal(0.0, 0.3, (T - 1, 2))
+    K = rng.normal(0.0, 0.2, (T - 1, 2, 8))
+    alpha = np.maximum(0.5 ** np.arange(R), 1.0e-5)
+    return x1, ubar, K, k, alpha
+
+
+def planar_push_rollout_inputs(R, T=26, h=0.1, seed=0):
+    """BASELINE.json configs[2]: planar push `rotate`, T = 26, R rollouts.  x1 and ū follow examples/planar_push.jl:46-47,112;
+    every rollout gets its own seeded perturbation of the nominal controls."""
+    rng = np.random.default_rng(seed)
+    r_dim = 0.1
+    q = np.array([0.0, 0.0, 0.0, -r_dim - 1.0e-8, -0.01])
+    x1 = np.tile(np.concatenate([q, q]), (R, 1))
+    nom = np.array([[1.0, 0.0] if t < 4 else [0.5, 0.0] if t < 9 else [0.0, 0.0] for t in range(T - 1)])
+    ubar = nom[None] + rng.normal(0.0, 0.05, (R, T - 1, 2))
+    return np.ascontiguousarray(x1), np.ascontiguousarray(ubar)
+
+
 def bundle_perturbations(ncol, N=64, eps=1.0e-4, seed=0):
     """One-hot perturbations η_i = ε·randn()·e_j (src/gradient_bundle.jl:49-54); the first ncol samples cover every coordinate
     once so the least-squares Hessian is never singular (the reference leaves that to chance)."""

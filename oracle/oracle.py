@@ -120,5 +120,31 @@ def least_squares(fz, feta, eta):
     return rc, theta.reshape(nz, ny).T   # reshape(θ, ny, nz) column-major
 
 
+def rollout_batch(model, x1, ubar, h, kappa_tol, xbar=None, K=None, k=None, alpha=None, fric=None, r_tol=1e-8):
+    """Restatement of the reference's rollout loop: iLQR.rollout(model, x1, ū) (x[t+1] = f(x[t], ū[t]); reference
+    examples/cartpole.jl:79) and the forward pass of IterativeLQR (u[t] = ū[t] + α k[t] + K[t](x[t] − x̄[t]); external package,
+    step sizes α ≥ α_min of examples/cartpole.jl:86), with f of reference src/dynamics.jl:81-94 — one eval-simulator step per
+    knot point.  x1: [R, 2nq]; ubar: [T-1, nu] or [R, T-1, nu].  Returns X [R, T, 2nq], U [R, T-1, nu], status [R, T-1]."""
+    nq, nu, nz, nth = dims(model)
+    x1 = np.ascontiguousarray(x1, dtype=np.float64).reshape(-1, 2 * nq); R = x1.shape[0]
+    ubar = np.asarray(ubar, dtype=np.float64)
+    S = ubar.shape[-2]; T = S + 1
+    X = np.zeros((R, T, 2 * nq)); U = np.zeros((R, S, nu)); st = np.zeros((R, S), dtype=np.int32)
+    al = np.ones(R) if alpha is None else np.asarray(alpha, dtype=np.float64)
+    X[:, 0] = x1
+    for t in range(S):
+        u = np.broadcast_to(ubar[t] if ubar.ndim == 2 else ubar[:, t], (R, nu)).copy()
+        if k is not None:
+            u = u + al[:, None] * np.asarray(k)[t][None, :]
+        if K is not None:
+            u = u + np.einsum("uj,rj->ru", np.asarray(K)[t], X[:, t] - np.asarray(xbar)[t][None, :])
+        U[:, t] = u
+        o = step_batch(model, X[:, t, :nq], X[:, t, nq:], u, h, kappa_tol, False, fric=fric, r_tol=r_tol, diagnostics=False)
+        X[:, t + 1, :nq] = X[:, t, nq:]
+        X[:, t + 1, nq:] = o["q3"]
+        st[:, t] = o["status"]
+    return X, U, st
+
+
 def num_threads():
     return lib().od_oracle_num_threads()

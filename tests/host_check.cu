@@ -40,6 +40,28 @@ extern "C" int hc_contact_step(int model, int B, const double* q1, const double*
     return 0;
 }
 
+template <class M> static void run_rollout(const RolloutArgs& a, int reg) {
+    if (reg) { alignas(16) double ws[ContactIP<M, 1, 1, true>::WS]; for (int r = 0; r < a.R; ++r) contact_rollout_one<M, 1, 1, true>(a, r, ws, 0, 0u); }
+    else { alignas(16) double ws[ContactIP<M>::WS]; for (int r = 0; r < a.R; ++r) contact_rollout_one<M, 1, 1, false>(a, r, ws, 0, 0u); }
+}
+extern "C" int hc_contact_rollout(int model, int R, int T, const double* x1, const double* ubar, long long ubar_stride, const double* xbar, const double* K,
+                                  const double* kff, const double* alpha, double h, const double* fric, double r_tol, double k_eval,
+                                  double* X, double* U, int* status, int reg) {
+    RolloutArgs a; memset(&a, 0, sizeof(a));
+    a.R = R; a.T = T; a.x1 = x1; a.ubar = ubar; a.ubar_stride = ubar_stride; a.xbar = xbar; a.K = K; a.kff = kff; a.alpha = alpha; a.X = X; a.U = U;
+    a.status = status; a.h = h;
+    for (int k = 0; k < 4; ++k) a.fric[k] = fric ? fric[k] : 0.0;
+    a.opts.r_tol = r_tol; a.opts.kappa_eval_tol = k_eval; a.opts.kappa_grad_tol = k_eval; a.opts.ls_scale = 0.5; a.opts.max_iter = 100; a.opts.max_ls = 25;
+    switch (model) {
+        case 0: run_rollout<AcrobotImpactModel>(a, reg); break;
+        case 2: run_rollout<CartpoleFrictionModel>(a, reg); break;
+        case 4: run_rollout<PlanarPushModel>(a, 0); break;
+        case 5: run_rollout<HopperModel>(a, reg); break;
+        default: return 1;
+    }
+    return 0;
+}
+
 extern "C" int hc_rocket(int B, const double* x, const double* u, double h, double u_max, int proj, int want_grad, int proj_only,
                          double* y, double* dx, double* du, double* uproj, double* duproj, int* status, int* iters) {
     RocketArgs a; memset(&a, 0, sizeof(a));

@@ -58,6 +58,28 @@ def step(model, q1, q2, u, h, k_eval=1e-4, k_grad=1e-3, fric=None, want_eval=Tru
     return dict(q3=q3, dq1=dq1, dq2=dq2, du=du, status=st, st_eval=st & 15, st_grad=(st >> 4) & 15, it_eval=it & 0xFFFF, it_grad=(it >> 16) & 0xFFFF)
 
 
+def rollout(model, x1, ubar, h, xbar=None, K=None, kff=None, alpha=None, k_eval=1e-4, fric=None, reg=False):
+    """Product rollout template on the host: returns X [R,T,2nq], U [R,T-1,nu], status [R,T-1]."""
+    nq, nu = DIMS[model]; nx = 2 * nq
+    x1 = np.ascontiguousarray(x1, dtype=np.float64).reshape(-1, nx); R = x1.shape[0]
+    ubar = np.ascontiguousarray(ubar, dtype=np.float64)
+    per = ubar.ndim == 3
+    S = ubar.shape[-2]; T = S + 1
+    c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+    xbar, K, kff, alpha = c(xbar), c(K), c(kff), c(alpha)
+    fr = np.zeros(4)
+    default = {"hopper": [0.5, 0.5], "cartpole_friction": [0.1, 0.1]}.get(model)
+    if fric is None and default is not None:
+        fric = default
+    if fric is not None:
+        fr[:len(fric)] = fric
+    X = np.zeros((R, T, nx)); U = np.zeros((R, S, nu)); st = np.zeros((R, S), dtype=np.int32)
+    rc = lib().hc_contact_rollout(MODELS[model], R, T, _p(x1), _p(ubar), C.c_longlong(S * nu if per else 0), _p(xbar), _p(K), _p(kff), _p(alpha),
+                                  C.c_double(h), _p(fr), C.c_double(1e-8), C.c_double(k_eval), _p(X), _p(U), _p(st, C.c_int), int(reg))
+    assert rc == 0
+    return X, U, st
+
+
 def rocket(x, u, h, u_max, proj, want_grad=True, proj_only=False):
     x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 12); B = x.shape[0]
     u = np.ascontiguousarray(u, dtype=np.float64).reshape(B, 3)

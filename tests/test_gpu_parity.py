@@ -179,3 +179,54 @@ def test_device_resident_packed_path_and_launch_accounting(od):
     torch.cuda.synchronize()
     assert dyn.launch_count() == n0 + 1
     assert np.array_equal(out.cpu().numpy(), ref) and np.array_equal(st.cpu().numpy(), st_ref)
+
+
+def _check_rollout(O, name, X, U, st, h, ke, fric):
+    """One-step parity along the GPU trajectory: X[t+1] = f(X[t], U[t]) against the oracle's step on the same (x, u) — 1e-8."""
+    R, T, nx = X.shape
+    nq = nx // 2
+    assert np.array_equal(X[:, 1:, :nq], X[:, :-1, nq:])                  # d[1:nq] = q2  (src/dynamics.jl:90)
+    Xf, Uf = X[:, :-1].reshape(-1, nx), U.reshape(R * (T - 1), -1)
+    o = O.step_batch(name, Xf[:, :nq], Xf[:, nq:], Uf, h, ke, False, fric=fric)
+    ok = (o["status"] == 0) & (st.reshape(-1) == 0) & (o["margin"] > 1e-6) & (o["iters"] <= 30)
+    assert ok.mean() > 0.95, ok.mean()
+    err = np.abs(o["q3"] - X[:, 1:, nq:].reshape(-1, nq)).max(1)
+    bad = ok & ~(err <= Q3_TOL)
+    assert not (bad & ~(o["q_uncertainty"] > 1e-7)).any() and bad.mean() <= 0.005, (bad.sum(), np.nanmax(err[ok]))
+    return float(err[ok & ~bad].max())
+
+
+def test_rollouts_match_oracle_hopper_forward_pass(od, O):
+    """iLQR forward pass (examples/hopper.jl:272-292): 16 Armijo step sizes of one closed-loop policy, T = 21, one launch."""
+    h = 0.05
+    x1, ubar, K, k, alpha = od.workloads.hopper_rollout_inputs(16, T=21, h=h, seed=3)
+    dyn = make_dyn(od, "hopper")
+    xbar = np.stack(od.rollout(dyn, x1, ubar))                           # iLQR.rollout(model, x1, ū)
+    Xo, Uo, sto = O.rollout_batch("hopper", x1[None], ubar, h, 1e-4)
+    assert np.abs(xbar - Xo[0]).max() < 1e-7
+    n0 = dyn.launch_count()
+    X, U, st = od.rollout_batch(dyn, x1, ubar, xbar=xbar, K=K, k=k, alpha=alpha, return_status=True)
+    assert dyn.launch_count() == n0 + 1                                   # (T−1)·R = 320 calls of f in the reference
+    e1 = _check_rollout(O, "hopper", X, U, st, h, 1e-4, None)
+    Xo, Uo, sto = O.rollout_batch("hopper", np.tile(x1, (16, 1)), ubar, h, 1e-4, xbar=xbar, K=K, k=k, alpha=alpha)
+    print("hopper forward pass: one-step max|q3-oracle|=%.2e  trajectory max|X-oracle|=%.2e" % (e1, np.abs(X - Xo).max()))
+    assert np.abs(X - Xo).max() < 1e-6 and np.abs(U - Uo).max() < 1e-6
+    assert np.abs(X[-1] - xbar).max() < 1e-4                              # α = 1e-5 ≈ the nominal trajectory
+
+
+@pytest.mark.parametrize("name", ["planar_push", "cartpole_friction", "acrobot_impact"])
+def test_rollouts_match_oracle_other_models(od, O, name):
+    """BASELINE.json configs[2] (planar push rotate, T = 26, 1024 rollouts, per-rollout controls) and the examples' other rollouts."""
+    gen, h, ke, kg, fric, _ = CONFIGS[name]
+    dyn = make_dyn(od, name)
+    if name == "planar_push":
+        x1, ubar = od.workloads.planar_push_rollout_inputs(1024, T=26, h=h, seed=1)
+    else:
+        T, R = 51, 64                                                     # examples/cartpole.jl:15, BASELINE.json configs[0..1]
+        q1, q2, u = gen(R, h=h, seed=5)
+        x1 = np.concatenate([q1, q2], axis=1)
+        ubar = 0.3 * np.random.default_rng(7).normal(size=(R, T - 1, dyn.nu))
+    X, U, st = od.rollout_batch(dyn, x1, ubar, return_status=True)
+    assert np.array_equal(U, ubar) and np.array_equal(X[:, 0], x1)
+    e1 = _check_rollout(O, name, X, U, st, h, ke, fric)
+    print("%s rollouts %s: one-step max|q3-oracle|=%.2e" % (name, X.shape, e1))

@@ -139,3 +139,38 @@ def test_state_to_configuration():
     x = [np.array([1.0, 2.0, 3.0, 4.0]), np.array([3.0, 4.0, 5.0, 6.0])]
     q = state_to_configuration(x)
     assert [list(v) for v in q] == [[1.0, 2.0], [3.0, 4.0], [5.0, 6.0]]
+
+
+def _rollout_agreement(name, X, U, st, Xo, Uo, sto, h, ke, fric):
+    """One-step consistency along the product's own trajectory (1e-8), and whole-trajectory agreement with the oracle rollout."""
+    nq = X.shape[2] // 2
+    assert (st == 0).mean() > 0.99 and (sto == 0).mean() > 0.99
+    R, T, _ = X.shape
+    assert np.array_equal(X[:, 1:, :nq], X[:, :-1, nq:])                  # d[1:nq] = q2  (src/dynamics.jl:90)
+    Xf, Uf = X[:, :-1].reshape(-1, 2 * nq), U.reshape(R * (T - 1), -1)
+    o = O.step_batch(name, Xf[:, :nq], Xf[:, nq:], Uf, h, ke, False, fric=fric)
+    ok = (o["status"] == 0) & (st.reshape(-1) == 0) & (o["margin"] > 1e-6) & (o["iters"] <= 30)
+    assert ok.mean() > 0.95
+    bad = ok & ~(np.abs(o["q3"] - X[:, 1:, nq:].reshape(-1, nq)).max(1) <= 1e-8)
+    assert not (bad & ~(o["q_uncertainty"] > 1e-7)).any() and bad.mean() <= 0.005
+    return float(np.abs(X - Xo).max()), float(np.abs(U - Uo).max())
+
+
+@pytest.mark.parametrize("reg", [False, True])
+def test_rollout_template_matches_oracle_rollout(reg):
+    """contact_rollout_one (the code of contact_rollout_kernel) on the host: iLQR.rollout + closed-loop forward pass, hopper."""
+    h = 0.05
+    x1, ubar, K, k, alpha = W.hopper_rollout_inputs(8, T=21, h=h, seed=3)
+    alpha[-1] = 1.0e-5                                                                 # α_min of examples/hopper.jl:277
+    Xn, _, _ = O.rollout_batch("hopper", x1[None], ubar, h, 1e-4)                      # nominal open-loop rollout = x̄
+    xbar = Xn[0]
+    x1s = np.tile(x1, (8, 1))
+    X, U, st = H.rollout("hopper", x1s, ubar, h, xbar=xbar, K=K, kff=k, alpha=alpha, reg=reg)
+    Xo, Uo, sto = O.rollout_batch("hopper", x1s, ubar, h, 1e-4, xbar=xbar, K=K, k=k, alpha=alpha)
+    ex, eu = _rollout_agreement("hopper", X, U, st, Xo, Uo, sto, h, 1e-4, None)
+    assert ex < 1e-6 and eu < 1e-6, (ex, eu)
+    # α → 0 reproduces the nominal trajectory
+    assert np.abs(X[-1] - xbar).max() < 1e-4
+    # open loop with the shared controls: every rollout identical to the nominal one
+    X0, U0, st0 = H.rollout("hopper", x1s[:2], ubar, h, reg=reg)
+    assert np.abs(X0[0] - xbar).max() < 1e-8 and np.array_equal(X0[0], X0[1]) and np.array_equal(U0[0], ubar)
