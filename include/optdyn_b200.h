@@ -106,6 +106,18 @@ int od_rollout_batch_device(od_handle* hd, int R, int T, const double* x1, const
                             const double* xbar, const double* K, const double* kff, const double* alpha, double* X, double* U,
                             int32_t* status, int32_t* iters);
 
+/* Batched Riccati backward pass — the consumer of fx / fu in the outer solver (IterativeLQR's backward pass inside iLQR.solve!,
+ * reference examples/hopper.jl:292; sequential in t, one warp per trajectory, NT trajectories per launch).
+ * jac: NT×(T−1) packed output rows of od_step_grad_packed (fx = [0 I; ∂q3/∂q1 ∂q3/∂q2], fu = [0; ∂q3/∂u1], src/dynamics.jl:105-125);
+ * cost expansion along the trajectory, n = 2nq, m = nu: lx NT×T×n, lu NT×(T−1)×m, lxx NT×T×n×n, luu NT×(T−1)×m×m,
+ * lux NT×(T−1)×m×n (NULL = 0); reg is added to the diagonal of Quu.
+ * Out: K NT×(T−1)×m×n row-major [t][control][state] and k NT×(T−1)×m — the layout od_rollout_batch takes — dV NT×2
+ * (Σ kᵀQu, ½ Σ kᵀQuu k; may be NULL), status NT (1 = a Quu was not positive definite; that step's gains are zero; may be NULL). */
+int od_riccati_batch(od_handle* hd, int NT, int T, const double* jac, const double* lx, const double* lu, const double* lxx,
+                     const double* luu, const double* lux, double reg, double* K, double* k, double* dV, int32_t* status);
+int od_riccati_batch_device(od_handle* hd, int NT, int T, const double* jac, const double* lx, const double* lu, const double* lxx,
+                            const double* luu, const double* lux, double reg, double* K, double* k, double* dV, int32_t* status);
+
 /* Gradient bundle — gradient!(eval_sim, gb, q1, q2, u1), reference src/gradient_bundle.jl:87-104: one nominal and N perturbed
  * eval-sim steps per problem ((N+1)·B solves in one launch), then the least-squares fit of src/ls.jl:44-60 in closed form
  * (normal equations).  eta: N×(2nq+nu) perturbations shared by the batch (host).  dz: B×(nq×(2nq+nu)) column-major (host).

@@ -7,9 +7,10 @@ from .gradient_bundle import GradientBundle, gradient, gradient_batch, fx_gb, fu
 from .rocket import (RocketInfo, f_rocket, fx_rocket, fu_rocket, soc_projection, soc_projection_gradient, f_rocket_proj, fx_rocket_proj,
                      fu_rocket_proj)
 from .rollout import rollout, rollout_batch
+from .riccati import backward_pass_batch
 from . import workloads
 
 __all__ = ["ImplicitDynamics", "Model", "f", "fx", "fu", "state_to_configuration", "GradientBundle", "gradient", "gradient_batch", "fx_gb",
            "fu_gb", "RocketInfo", "f_rocket", "fx_rocket", "fu_rocket", "soc_projection", "soc_projection_gradient", "f_rocket_proj",
            "fx_rocket_proj", "fu_rocket_proj", "acrobot_impact", "acrobot_nominal", "cartpole_friction", "cartpole_frictionless",
-           "planarpush", "hopper", "rocket", "rollout", "rollout_batch", "workloads"]
+           "planarpush", "hopper", "rocket", "rollout", "rollout_batch", "backward_pass_batch", "workloads"]

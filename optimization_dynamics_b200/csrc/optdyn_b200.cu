@@ -10,6 +10,7 @@
 #include "models.cuh"
 #include "dense_ip.cuh"
 #include "rocket.cuh"
+#include "riccati.cuh"
 
 namespace od {
 
@@ -453,6 +454,61 @@ int od_rollout_batch(od_handle* hd, int R, int T, const double* x1, const double
     OD_CUDA(cudaMemcpyAsync(X, d_X, sizeof(double) * n_X, cudaMemcpyDeviceToHost, hd->stream));
     if (U) OD_CUDA(cudaMemcpyAsync(U, d_U, sizeof(double) * n_U, cudaMemcpyDeviceToHost, hd->stream));
     if (status) OD_CUDA(cudaMemcpyAsync(status, hd->st.p, sizeof(int32_t) * (size_t)R * S, cudaMemcpyDeviceToHost, hd->stream));
+    OD_CUDA(cudaStreamSynchronize(hd->stream));
+    return 0;
+}
+
+int od_riccati_batch_device(od_handle* hd, int NT, int T, const double* jac, const double* lx, const double* lu, const double* lxx,
+                            const double* luu, const double* lux, double reg, double* K, double* k, double* dV, int32_t* status) {
+    if (!hd) return fail("null handle");
+    if (hd->model == OD_ROCKET) return fail("od_riccati_batch: contact models only (state x = [q1; q2])");
+    Dims d; dims_of(hd->model, &d);
+    if (NT <= 0 || T <= 1) return 0;
+    if (!jac || !lx || !lu || !lxx || !luu || !K || !k) return fail("od_riccati_batch: jac, lx, lu, lxx, luu, K and k are required");
+    if (2 * d.nq > RICCATI_MAX_N || d.nu > RICCATI_MAX_M) return fail("od_riccati_batch: model too large");
+    OD_CUDA(cudaSetDevice(hd->device));
+    RiccatiArgs a; memset(&a, 0, sizeof(a));
+    a.NT = NT; a.T = T; a.nq = d.nq; a.nu = d.nu; a.jac = jac; a.lx = lx; a.lu = lu; a.lxx = lxx; a.luu = luu; a.lux = lux; a.reg = reg;
+    a.K = K; a.k = k; a.dV = dV; a.status = status;
+    constexpr int WARPS = 2;
+    const size_t smem = sizeof(double) * WARPS * riccati_ws(2 * d.nq, d.nu);
+    riccati_kernel<WARPS><<<(NT + WARPS - 1) / WARPS, 32 * WARPS, smem, hd->stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("riccati_kernel launch", e);
+    hd->launches++;
+    return 0;
+}
+
+int od_riccati_batch(od_handle* hd, int NT, int T, const double* jac, const double* lx, const double* lu, const double* lxx,
+                     const double* luu, const double* lux, double reg, double* K, double* k, double* dV, int32_t* status) {
+    if (!hd) return fail("null handle");
+    if (hd->model == OD_ROCKET) return fail("od_riccati_batch: contact models only (state x = [q1; q2])");
+    Dims d; dims_of(hd->model, &d);
+    if (NT <= 0 || T <= 1) return 0;
+    if (!jac || !lx || !lu || !lxx || !luu || !K || !k) return fail("od_riccati_batch: jac, lx, lu, lxx, luu, K and k are required");
+    OD_CUDA(cudaSetDevice(hd->device));
+    const size_t n = 2 * d.nq, m = d.nu, S = T - 1, roww = d.nq + d.nq * (n + m);
+    const size_t c_jac = (size_t)NT * S * roww, c_lx = (size_t)NT * T * n, c_lu = (size_t)NT * S * m, c_lxx = (size_t)NT * T * n * n;
+    const size_t c_luu = (size_t)NT * S * m * m, c_lux = lux ? (size_t)NT * S * m * n : 0;
+    const size_t c_K = (size_t)NT * S * m * n, c_k = (size_t)NT * S * m, c_dV = (size_t)NT * 2;
+    OD_CUDA(hd->in.reserve(sizeof(double) * (c_jac + c_lx + c_lu + c_lxx + c_luu + c_lux)));
+    OD_CUDA(hd->out.reserve(sizeof(double) * (c_K + c_k + c_dV)));
+    OD_CUDA(hd->st.reserve(sizeof(int32_t) * NT));
+    double* p = (double*)hd->in.p;
+    double* d_jac = p; p += c_jac; double* d_lx = p; p += c_lx; double* d_lu = p; p += c_lu; double* d_lxx = p; p += c_lxx;
+    double* d_luu = p; p += c_luu; double* d_lux = lux ? p : nullptr;
+    OD_CUDA(cudaMemcpyAsync(d_jac, jac, sizeof(double) * c_jac, cudaMemcpyHostToDevice, hd->stream));
+    OD_CUDA(cudaMemcpyAsync(d_lx, lx, sizeof(double) * c_lx, cudaMemcpyHostToDevice, hd->stream));
+    OD_CUDA(cudaMemcpyAsync(d_lu, lu, sizeof(double) * c_lu, cudaMemcpyHostToDevice, hd->stream));
+    OD_CUDA(cudaMemcpyAsync(d_lxx, lxx, sizeof(double) * c_lxx, cudaMemcpyHostToDevice, hd->stream));
+    OD_CUDA(cudaMemcpyAsync(d_luu, luu, sizeof(double) * c_luu, cudaMemcpyHostToDevice, hd->stream));
+    if (lux) OD_CUDA(cudaMemcpyAsync(d_lux, lux, sizeof(double) * c_lux, cudaMemcpyHostToDevice, hd->stream));
+    double* d_K = (double*)hd->out.p; double* d_k = d_K + c_K; double* d_dV = d_k + c_k;
+    if (od_riccati_batch_device(hd, NT, T, d_jac, d_lx, d_lu, d_lxx, d_luu, d_lux, reg, d_K, d_k, d_dV, (int32_t*)hd->st.p)) return 1;
+    OD_CUDA(cudaMemcpyAsync(K, d_K, sizeof(double) * c_K, cudaMemcpyDeviceToHost, hd->stream));
+    OD_CUDA(cudaMemcpyAsync(k, d_k, sizeof(double) * c_k, cudaMemcpyDeviceToHost, hd->stream));
+    if (dV) OD_CUDA(cudaMemcpyAsync(dV, d_dV, sizeof(double) * c_dV, cudaMemcpyDeviceToHost, hd->stream));
+    if (status) OD_CUDA(cudaMemcpyAsync(status, hd->st.p, sizeof(int32_t) * NT, cudaMemcpyDeviceToHost, hd->stream));
     OD_CUDA(cudaStreamSynchronize(hd->stream));
     return 0;
 }

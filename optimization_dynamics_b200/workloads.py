@@ -107,6 +107,23 @@ def planar_push_rollout_inputs(R, T=26, h=0.1, seed=0):
     return np.ascontiguousarray(x1), np.ascontiguousarray(ubar)
 
 
+def quadratic_cost_expansion(X, U, x_goal, q_diag, r_diag, qT_diag, seed=None):
+    """Cost expansion of the tracking objective the reference examples use (quadratic in x − x_goal and u, e.g.
+    examples/cartpole.jl:50-66): lx, lu, lxx, luu (and a small seeded cross term lux when seed is given) along NT trajectories.
+    X: [NT, T, n], U: [NT, T-1, m]."""
+    NT, T, n = X.shape; m = U.shape[2]
+    Q = np.diag(np.broadcast_to(q_diag, (n,)).astype(np.float64)); QT = np.diag(np.broadcast_to(qT_diag, (n,)).astype(np.float64))
+    Rm = np.diag(np.broadcast_to(r_diag, (m,)).astype(np.float64))
+    lxx = np.tile(Q, (NT, T, 1, 1)); lxx[:, -1] = QT
+    lx = np.einsum("atij,atj->ati", lxx, X - np.asarray(x_goal)[None, None, :])
+    luu = np.tile(Rm, (NT, T - 1, 1, 1))
+    lu = np.einsum("atij,atj->ati", luu, U)
+    lux = None
+    if seed is not None:
+        lux = 1.0e-2 * np.random.default_rng(seed).normal(size=(NT, T - 1, m, n))
+    return lx, lu, lxx, luu, lux
+
+
 def bundle_perturbations(ncol, N=64, eps=1.0e-4, seed=0):
     """One-hot perturbations η_i = ε·randn()·e_j (src/gradient_bundle.jl:49-54); the first ncol samples cover every coordinate
     once so the least-squares Hessian is never singular (the reference leaves that to chance)."""

@@ -146,5 +146,40 @@ def rollout_batch(model, x1, ubar, h, kappa_tol, xbar=None, K=None, k=None, alph
     return X, U, st
 
 
+def fx_fu_from_packed(row, nq, nu):
+    """fx = [0 I; ∂q3∂q1 ∂q3∂q2], fu = [0; ∂q3∂u1] from one packed output row (reference src/dynamics.jl:105-111,125)."""
+    n = 2 * nq
+    d1 = row[nq:nq + nq * nq].reshape(nq, nq).T
+    d2 = row[nq + nq * nq:nq + 2 * nq * nq].reshape(nq, nq).T
+    du = row[nq + 2 * nq * nq:].reshape(nu, nq).T
+    fx = np.zeros((n, n)); fx[:nq, nq:] = np.eye(nq); fx[nq:, :nq] = d1; fx[nq:, nq:] = d2
+    fu = np.zeros((n, nu)); fu[nq:] = du
+    return fx, fu
+
+
+def backward_pass(jac, lx, lu, lxx, luu, lux, nq, nu, reg=0.0):
+    """Restatement of the iLQR backward pass (IterativeLQR.jl, external to the reference tree; textbook Riccati recursion without
+    regularisation schedule) for ONE trajectory: returns K [T-1,m,n], k [T-1,m], dV [2], status."""
+    S = jac.shape[0]; n = 2 * nq
+    P = lxx[S].copy(); p = lx[S].copy()
+    K = np.zeros((S, nu, n)); k = np.zeros((S, nu)); dV = np.zeros(2); status = 0
+    for t in range(S - 1, -1, -1):
+        fx, fu = fx_fu_from_packed(jac[t], nq, nu)
+        Qx = lx[t] + fx.T @ p; Qu = lu[t] + fu.T @ p
+        Qxx = lxx[t] + fx.T @ P @ fx
+        Quu = luu[t] + fu.T @ P @ fu + reg * np.eye(nu)
+        Qux = (0.0 if lux is None else lux[t]) + fu.T @ P @ fx
+        try:
+            np.linalg.cholesky(Quu)
+            Kt = -np.linalg.solve(Quu, Qux); kt = -np.linalg.solve(Quu, Qu)
+        except np.linalg.LinAlgError:
+            status = 1; Kt = np.zeros((nu, n)); kt = np.zeros(nu)
+        K[t] = Kt; k[t] = kt
+        dV += [kt @ Qu, 0.5 * kt @ Quu @ kt]
+        P = Qxx + Kt.T @ Quu @ Kt + Kt.T @ Qux + Qux.T @ Kt
+        p = Qx + Kt.T @ Quu @ kt + Kt.T @ Qu + Qux.T @ kt
+    return K, k, dV, status
+
+
 def num_threads():
     return lib().od_oracle_num_threads()

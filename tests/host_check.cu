@@ -5,6 +5,8 @@
 // Built by tests/conftest.py with:  nvcc -O2 -std=c++17 -Xcompiler -fPIC -shared -o tests/_build/libhostcheck.so tests/host_check.cu
 #include <string.h>
 #include "../optimization_dynamics_b200/csrc/rocket.cuh"
+#include "../optimization_dynamics_b200/csrc/riccati.cuh"
+#include <vector>
 
 using namespace od;
 
@@ -59,6 +61,16 @@ extern "C" int hc_contact_rollout(int model, int R, int T, const double* x1, con
         case 5: run_rollout<HopperModel>(a, reg); break;
         default: return 1;
     }
+    return 0;
+}
+
+extern "C" int hc_riccati(int NT, int T, int nq, int nu, const double* jac, const double* lx, const double* lu, const double* lxx, const double* luu,
+                          const double* lux, double reg, double* K, double* k, double* dV, int* status) {
+    RiccatiArgs a; memset(&a, 0, sizeof(a));
+    a.NT = NT; a.T = T; a.nq = nq; a.nu = nu; a.jac = jac; a.lx = lx; a.lu = lu; a.lxx = lxx; a.luu = luu; a.lux = lux; a.reg = reg;
+    a.K = K; a.k = k; a.dV = dV; a.status = status;
+    std::vector<double> ws(riccati_ws(2 * nq, nu));
+    for (int tr = 0; tr < NT; ++tr) riccati_one(a, tr, ws.data(), 0, 1);
     return 0;
 }
 

@@ -80,6 +80,16 @@ def rollout(model, x1, ubar, h, xbar=None, K=None, kff=None, alpha=None, k_eval=
     return X, U, st
 
 
+def riccati(jac, lx, lu, lxx, luu, lux, nq, nu, reg=0.0):
+    c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+    jac, lx, lu, lxx, luu, lux = c(jac), c(lx), c(lu), c(lxx), c(luu), c(lux)
+    NT, S = jac.shape[0], jac.shape[1]; n = 2 * nq
+    K = np.zeros((NT, S, nu, n)); k = np.zeros((NT, S, nu)); dV = np.zeros((NT, 2)); st = np.zeros(NT, dtype=np.int32)
+    rc = lib().hc_riccati(NT, S + 1, nq, nu, _p(jac), _p(lx), _p(lu), _p(lxx), _p(luu), _p(lux), C.c_double(reg), _p(K), _p(k), _p(dV), _p(st, C.c_int))
+    assert rc == 0
+    return K, k, dV, st
+
+
 def rocket(x, u, h, u_max, proj, want_grad=True, proj_only=False):
     x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 12); B = x.shape[0]
     u = np.ascontiguousarray(u, dtype=np.float64).reshape(B, 3)

@@ -230,3 +230,34 @@ def test_rollouts_match_oracle_other_models(od, O, name):
     assert np.array_equal(U, ubar) and np.array_equal(X[:, 0], x1)
     e1 = _check_rollout(O, name, X, U, st, h, ke, fric)
     print("%s rollouts %s: one-step max|q3-oracle|=%.2e" % (name, X.shape, e1))
+
+
+def test_riccati_backward_pass_and_full_ilqr_iteration(od, O):
+    """Derivative sweep → batched Riccati backward pass → line-search rollouts, all through the C ABI, against the oracle's
+    restatement of each stage (hopper, 8 trajectories of T = 21)."""
+    h, NT, T = 0.05, 8, 21
+    dyn = make_dyn(od, "hopper")
+    x1, ubar, _, k0, alpha = od.workloads.hopper_rollout_inputs(NT, T=T, h=h, seed=4)
+    X, U, st = od.rollout_batch(dyn, x1, ubar, k=k0, alpha=alpha, return_status=True)          # NT different nominal trajectories
+    assert (st == 0).all()
+    xin = np.concatenate([X[:, :-1].reshape(-1, 8), U.reshape(-1, 2)], axis=1)
+    rows, st2 = dyn.step_grad_packed(xin)                                                       # the derivative sweep
+    assert (st2 == 0).all()
+    jac = rows.reshape(NT, T - 1, 44)
+    x_goal = np.concatenate([[1.0, 0.55, 0.0, 0.5]] * 2)
+    lx, lu, lxx, luu, lux = od.workloads.quadratic_cost_expansion(X, U, x_goal, 1.0e-1, 1.0e-1, 10.0, seed=1)
+    K, k, dV, sr = od.backward_pass_batch(dyn, jac, lx, lu, lxx, luu, lux)
+    assert (sr == 0).all()
+    for a in range(NT):
+        Ko, ko, dVo, so = O.backward_pass(jac[a], lx[a], lu[a], lxx[a], luu[a], lux[a], 4, 2)
+        assert so == 0
+        assert np.abs(K[a] - Ko).max() <= 1e-9 * max(1.0, np.abs(Ko).max()) and np.abs(k[a] - ko).max() <= 1e-9 * max(1.0, np.abs(ko).max())
+        assert np.abs(dV[a] - dVo).max() <= 1e-9 * max(1.0, np.abs(dVo).max())
+    assert (dV[:, 0] < 0).all()                                                                 # descent direction
+    # forward pass of trajectory 0 with its gains: 8 step sizes in one launch; α = 1e-5 stays on the nominal trajectory
+    al = np.array([1.0, 0.5, 0.25, 0.125, 0.0625, 0.03125, 1e-3, 1e-5])
+    Xn, Un, sn = od.rollout_batch(dyn, X[0, 0], U[0], xbar=X[0], K=K[0], k=k[0], alpha=al, return_status=True)
+    assert np.abs(Xn[-1] - X[0]).max() < 1e-4
+    Xo, Uo, so = O.rollout_batch("hopper", np.tile(X[0, 0], (8, 1)), U[0], h, 1e-4, xbar=X[0], K=K[0], k=k[0], alpha=al)
+    ok = (sn == 0).all(axis=1) & (so == 0).all(axis=1)
+    assert ok.sum() >= 6 and np.abs(Xn - Xo)[ok].max() < 1e-6

@@ -174,3 +174,33 @@ def test_rollout_template_matches_oracle_rollout(reg):
     # open loop with the shared controls: every rollout identical to the nominal one
     X0, U0, st0 = H.rollout("hopper", x1s[:2], ubar, h, reg=reg)
     assert np.abs(X0[0] - xbar).max() < 1e-8 and np.array_equal(X0[0], X0[1]) and np.array_equal(U0[0], ubar)
+
+
+def _riccati_case(NT=6, T=21, seed=2):
+    """Jacobians along closed-loop hopper trajectories (oracle) + the tracking-cost expansion."""
+    h = 0.05
+    x1, ubar, K, k, alpha = W.hopper_rollout_inputs(NT, T=T, h=h, seed=seed)
+    X, U, st = O.rollout_batch("hopper", np.tile(x1, (NT, 1)), ubar, h, 1e-4, k=k, alpha=alpha)
+    Xf, Uf = X[:, :-1].reshape(-1, 8), U.reshape(-1, 2)
+    g = O.step_batch("hopper", Xf[:, :4], Xf[:, 4:], Uf, h, 1e-3, True, diagnostics=False)
+    jac = np.concatenate([g["q3"], g["dq1"].reshape(-1, 16), g["dq2"].reshape(-1, 16), g["du"].reshape(-1, 8)], axis=1).reshape(NT, T - 1, 44)
+    x_goal = np.concatenate([[1.0, 0.55, 0.0, 0.5]] * 2)
+    lx, lu, lxx, luu, lux = W.quadratic_cost_expansion(X, U, x_goal, 1.0e-1, 1.0e-1, 10.0, seed=seed)
+    return jac, lx, lu, lxx, luu, lux
+
+
+def test_riccati_template_matches_oracle_backward_pass():
+    """riccati_one (the code of riccati_kernel) on the host against the numpy restatement of the iLQR backward pass."""
+    jac, lx, lu, lxx, luu, lux = _riccati_case()
+    for cross, reg in ((lux, 0.0), (None, 1.0e-3)):
+        K, k, dV, st = H.riccati(jac, lx, lu, lxx, luu, cross, 4, 2, reg)
+        for a in range(jac.shape[0]):
+            Ko, ko, dVo, sto = O.backward_pass(jac[a], lx[a], lu[a], lxx[a], luu[a], None if cross is None else cross[a], 4, 2, reg)
+            assert sto == 0 and st[a] == 0
+            assert np.abs(K[a] - Ko).max() <= 1e-9 * max(1.0, np.abs(Ko).max()) and np.abs(k[a] - ko).max() <= 1e-9 * max(1.0, np.abs(ko).max())
+            assert np.abs(dV[a] - dVo).max() <= 1e-9 * max(1.0, np.abs(dVo).max())
+    # an indefinite Quu is reported, not silently inverted
+    luu_bad = luu.copy(); luu_bad[0, 5] = -1.0e3 * np.eye(2)
+    _, _, _, st = H.riccati(jac, lx, lu, lxx, luu_bad, None, 4, 2, 0.0)
+    assert st[0] == 1 and (st[1:] == 0).all()
+    assert O.backward_pass(jac[0], lx[0], lu[0], lxx[0], luu_bad[0], None, 4, 2)[3] == 1
