@@ -465,14 +465,16 @@ int od_riccati_batch_device(od_handle* hd, int NT, int T, const double* jac, con
     Dims d; dims_of(hd->model, &d);
     if (NT <= 0 || T <= 1) return 0;
     if (!jac || !lx || !lu || !lxx || !luu || !K || !k) return fail("od_riccati_batch: jac, lx, lu, lxx, luu, K and k are required");
-    if (2 * d.nq > RICCATI_MAX_N || d.nu > RICCATI_MAX_M) return fail("od_riccati_batch: model too large");
     OD_CUDA(cudaSetDevice(hd->device));
     RiccatiArgs a; memset(&a, 0, sizeof(a));
-    a.NT = NT; a.T = T; a.nq = d.nq; a.nu = d.nu; a.jac = jac; a.lx = lx; a.lu = lu; a.lxx = lxx; a.luu = luu; a.lux = lux; a.reg = reg;
+    a.NT = NT; a.T = T; a.jac = jac; a.lx = lx; a.lu = lu; a.lxx = lxx; a.luu = luu; a.lux = lux; a.reg = reg;
     a.K = K; a.k = k; a.dV = dV; a.status = status;
     constexpr int WARPS = 2;
-    const size_t smem = sizeof(double) * WARPS * riccati_ws(2 * d.nq, d.nu);
-    riccati_kernel<WARPS><<<(NT + WARPS - 1) / WARPS, 32 * WARPS, smem, hd->stream>>>(a);
+    const int grid = (NT + WARPS - 1) / WARPS;
+    if (d.nq == 2 && d.nu == 1) riccati_kernel<2, 1, WARPS><<<grid, 32 * WARPS, sizeof(double) * WARPS * Riccati<2, 1, 32>::WS, hd->stream>>>(a);
+    else if (d.nq == 4 && d.nu == 2) riccati_kernel<4, 2, WARPS><<<grid, 32 * WARPS, sizeof(double) * WARPS * Riccati<4, 2, 32>::WS, hd->stream>>>(a);
+    else if (d.nq == 5 && d.nu == 2) riccati_kernel<5, 2, WARPS><<<grid, 32 * WARPS, sizeof(double) * WARPS * Riccati<5, 2, 32>::WS, hd->stream>>>(a);
+    else return fail("od_riccati_batch: no instantiation for this model's dimensions");
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("riccati_kernel launch", e);
     hd->launches++;

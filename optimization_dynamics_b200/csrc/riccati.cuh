@@ -11,6 +11,11 @@
 //     fx = [0 I; ∂q3/∂q1 ∂q3/∂q2]  (2nq × 2nq),   fu = [0; ∂q3/∂u1]  (2nq × nu)          reference src/dynamics.jl:105-111,125
 // and writing the gains in the layout od_rollout_batch consumes (K: [t][control][state]) — sweep → backward pass → line-search
 // rollouts chain on one stream without the Jacobians ever visiting the host.
+//
+// The recursion is latency-bound (T−1 dependent steps of 8×8 products): dimensions are template parameters (constant index
+// arithmetic, unrolled dot products), the matrices live in shared memory with each lane owning fixed elements, the value function
+// ping-pongs between two buffers, and the global loads of step t−1 (Jacobian row, cost blocks) are issued into registers at the top
+// of step t so that their HBM/L2 latency overlaps step t's arithmetic.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -22,7 +27,7 @@
 namespace od {
 
 struct RiccatiArgs {
-    int NT, T, nq, nu;
+    int NT, T;
     const double* jac;        // NT × (T−1) packed rows, width nq + nq(2nq+nu)
     const double* lx;         // NT × T × n          (n = 2nq)
     const double* lu;         // NT × (T−1) × m      (m = nu)
@@ -36,135 +41,230 @@ struct RiccatiArgs {
     int* status;              // NT: 0 ok, 1 = some Quu not positive definite (gains of that step are zero), or null
 };
 
-constexpr int RICCATI_MAX_N = 12, RICCATI_MAX_M = 3;
-// workspace doubles per trajectory
-__host__ __device__ constexpr int riccati_ws(int n, int m) { return 5 * n * n + 5 * n * m + 3 * m * m + 4 * n + 4 * m + 8; }
-
 OD_HD void riccati_sync() {
 #ifdef __CUDA_ARCH__
     __syncwarp();
 #endif
 }
 
-// One trajectory; `lane`/`nl` = this thread's index and the number of cooperating threads (32 on the device, 1 on the host).
-OD_HD void riccati_one(const RiccatiArgs& a, const int tr, double* ws, const int lane, const int nl) {
-    const int nq = a.nq, m = a.nu, n = 2 * nq, T = a.T, S = T - 1;
-    const int roww = nq + nq * (n + m);
-    double* P = ws;                 // n×n   value Hessian at t+1
-    double* A = P + n * n;          // n×n   fx
-    double* PA = A + n * n;         // n×n   P fx
-    double* Qxx = PA + n * n;       // n×n
-    double* Pn = Qxx + n * n;       // n×n   value Hessian at t
-    double* Bm = Pn + n * n;        // n×m   fu
-    double* PB = Bm + n * m;        // n×m   P fu
-    double* Qux = PB + n * m;       // m×n
-    double* Kt = Qux + n * m;       // m×n
-    double* QK = Kt + n * m;        // m×n   Quu K
-    double* Quu = QK + n * m;       // m×m
-    double* Lc = Quu + m * m;       // m×m   Cholesky factor
-    double* sp = Lc + 2 * m * m;    // scalars
-    double* p = sp + 8;             // n     value gradient at t+1
-    double* pn = p + n;             // n
-    double* Qx = pn + n;            // n
-    double* Qu = Qx + n;            // m
-    double* kt = Qu + m;            // m
-    double* Qk = kt + m;            // m     Quu k
-    const double* lxT = a.lx + ((size_t)tr * T + S) * n;
-    const double* lxxT = a.lxx + ((size_t)tr * T + S) * n * n;
-    for (int e = lane; e < n * n; e += nl) P[e] = lxxT[e];
-    for (int e = lane; e < n; e += nl) p[e] = lxT[e];
-    double dv1 = 0.0, dv2 = 0.0;
-    int bad = 0;
-    for (int t = S - 1; t >= 0; --t) {
-        riccati_sync();
-        const double* row = a.jac + ((size_t)tr * S + t) * roww;
-        const double* d1 = row + nq; const double* d2 = d1 + nq * nq; const double* du = d2 + nq * nq;     // column-major blocks
-        for (int e = lane; e < n * n; e += nl) {
-            const int i = e / n, j = e % n;
-            double v;
-            if (i < nq) v = (j == i + nq) ? 1.0 : 0.0;
-            else v = (j < nq) ? d1[j * nq + (i - nq)] : d2[(j - nq) * nq + (i - nq)];
-            A[e] = v;
-        }
-        for (int e = lane; e < n * m; e += nl) { const int i = e / m, j = e % m; Bm[e] = (i < nq) ? 0.0 : du[j * nq + (i - nq)]; }
-        riccati_sync();
-        for (int e = lane; e < n * n; e += nl) { const int i = e / n, j = e % n; double s = 0.0; for (int l = 0; l < n; ++l) s += P[i * n + l] * A[l * n + j]; PA[e] = s; }
-        for (int e = lane; e < n * m; e += nl) { const int i = e / m, j = e % m; double s = 0.0; for (int l = 0; l < n; ++l) s += P[i * n + l] * Bm[l * m + j]; PB[e] = s; }
-        riccati_sync();
-        const double* lxt = a.lx + ((size_t)tr * T + t) * n;
-        const double* lut = a.lu + ((size_t)tr * S + t) * m;
-        const double* lxxt = a.lxx + ((size_t)tr * T + t) * n * n;
-        const double* luut = a.luu + ((size_t)tr * S + t) * m * m;
-        const double* luxt = a.lux ? a.lux + ((size_t)tr * S + t) * m * n : nullptr;
-        for (int e = lane; e < n * n; e += nl) { const int i = e / n, j = e % n; double s = lxxt[e]; for (int l = 0; l < n; ++l) s += A[l * n + i] * PA[l * n + j]; Qxx[e] = s; }
-        for (int e = lane; e < m * n; e += nl) { const int i = e / n, j = e % n; double s = luxt ? luxt[e] : 0.0; for (int l = 0; l < n; ++l) s += Bm[l * m + i] * PA[l * n + j]; Qux[e] = s; }
-        for (int e = lane; e < m * m; e += nl) { const int i = e / m, j = e % m; double s = luut[e] + (i == j ? a.reg : 0.0); for (int l = 0; l < n; ++l) s += Bm[l * m + i] * PB[l * m + j]; Quu[e] = s; }
-        for (int e = lane; e < n; e += nl) { double s = lxt[e]; for (int l = 0; l < n; ++l) s += A[l * n + e] * p[l]; Qx[e] = s; }
-        for (int e = lane; e < m; e += nl) { double s = lut[e]; for (int l = 0; l < n; ++l) s += Bm[l * m + e] * p[l]; Qu[e] = s; }
-        riccati_sync();
-        // Cholesky of Quu (m ≤ 3), redundantly in every thread; then thread j solves column j of −[Qux | Qu]
-        double Lr[RICCATI_MAX_M * RICCATI_MAX_M];
-        bool pd = true;
-        for (int i = 0; i < m; ++i) {
-            for (int j = 0; j <= i; ++j) {
-                double s = Quu[i * m + j];
-                for (int l = 0; l < j; ++l) s -= Lr[i * m + l] * Lr[j * m + l];
-                if (i == j) { pd = pd && (s > 0.0); Lr[i * m + i] = sqrt(s); }
-                else Lr[i * m + j] = s / Lr[j * m + j];
-            }
-        }
-        if (!pd) bad = 1;
-        for (int c = lane; c < n + 1; c += nl) {
-            double y[RICCATI_MAX_M];
-            for (int i = 0; i < m; ++i) {
-                double s = -((c < n) ? Qux[i * n + c] : Qu[i]);
-                for (int l = 0; l < i; ++l) s -= Lr[i * m + l] * y[l];
-                y[i] = s / Lr[i * m + i];
-            }
-            for (int i = m - 1; i >= 0; --i) {
-                double s = y[i];
-                for (int l = i + 1; l < m; ++l) s -= Lr[l * m + i] * y[l];
-                y[i] = s / Lr[i * m + i];
-            }
-            for (int i = 0; i < m; ++i) { const double v = pd ? y[i] : 0.0; if (c < n) Kt[i * n + c] = v; else kt[i] = v; }
-        }
-        riccati_sync();
-        for (int e = lane; e < m * n; e += nl) { const int i = e / n, j = e % n; double s = 0.0; for (int l = 0; l < m; ++l) s += Quu[i * m + l] * Kt[l * n + j]; QK[e] = s; }
-        for (int e = lane; e < m; e += nl) { double s = 0.0; for (int l = 0; l < m; ++l) s += Quu[e * m + l] * kt[l]; Qk[e] = s; }
-        riccati_sync();
-        for (int e = lane; e < n * n; e += nl) {
-            const int i = e / n, j = e % n;
-            double s = Qxx[e];
-            for (int l = 0; l < m; ++l) s += Kt[l * n + i] * QK[l * n + j] + Kt[l * n + i] * Qux[l * n + j] + Qux[l * n + i] * Kt[l * n + j];
-            Pn[e] = s;
-        }
-        for (int e = lane; e < n; e += nl) {
-            double s = Qx[e];
-            for (int l = 0; l < m; ++l) s += Kt[l * n + e] * Qk[l] + Kt[l * n + e] * Qu[l] + Qux[l * n + e] * kt[l];
-            pn[e] = s;
-        }
-        double* Ko = a.K + ((size_t)tr * S + t) * m * n;
-        double* ko = a.k + ((size_t)tr * S + t) * m;
-        for (int e = lane; e < m * n; e += nl) Ko[e] = Kt[e];
-        for (int e = lane; e < m; e += nl) ko[e] = kt[e];
-        for (int l = 0; l < m; ++l) { dv1 += kt[l] * Qu[l]; dv2 += 0.5 * kt[l] * Qk[l]; }
-        riccati_sync();
-        for (int e = lane; e < n * n; e += nl) P[e] = Pn[e];
-        for (int e = lane; e < n; e += nl) p[e] = pn[e];
-    }
-    if (lane == 0) {
-        if (a.dV) { a.dV[2 * (size_t)tr] = dv1; a.dV[2 * (size_t)tr + 1] = dv2; }
-        if (a.status) a.status[tr] = bad;
-    }
-}
+// NL cooperating threads (32 on the device, 1 in the host build of tests/host_check.cu).
+template <int NQ, int NU, int NL>
+struct Riccati {
+    static constexpr int N = 2 * NQ, M = NU, NN = N * N, NM = N * M, MM = M * M;
+    static constexpr int ROWW = NQ + NQ * (N + M);
+    static constexpr int E_NN = (NN + NL - 1) / NL, E_NM = (NM + NL - 1) / NL, E_N = (N + NL - 1) / NL, E_MM = (MM + NL - 1) / NL, E_M = (M + NL - 1) / NL;
+    // shared-memory workspace (doubles)
+    static constexpr int O_P0 = 0, O_P1 = O_P0 + NN, O_A = O_P1 + NN, O_PA = O_A + NN, O_QXX = O_PA + NN;
+    static constexpr int O_B = O_QXX + NN, O_PB = O_B + NM, O_QUX = O_PB + NM, O_K = O_QUX + NM, O_QK = O_K + NM;
+    static constexpr int O_QUU = O_QK + NM, O_p0 = O_QUU + MM, O_p1 = O_p0 + N, O_QX = O_p1 + N, O_QU = O_QX + N, O_k = O_QU + M, O_Qk = O_k + M;
+    static constexpr int WS = O_Qk + M;
 
-template <int WARPS>
+    struct Fetch { double a[E_NN], lxx[E_NN], b[E_NM], lux[E_NM], luu[E_MM], lx[E_N], lu[E_M]; };
+
+    // this lane's elements of fx, fu and of the cost expansion at knot point t (global loads only; nothing is consumed here)
+    OD_HD static void fetch(const RiccatiArgs& a, const int tr, const int t, const int lane, Fetch& f) {
+        const int S = a.T - 1;
+        const double* row = a.jac + ((size_t)tr * S + t) * ROWW;
+        const double* d1 = row + NQ; const double* du = d1 + 2 * NQ * NQ;     // column-major blocks ∂q3/∂q1 | ∂q3/∂q2 | ∂q3/∂u1
+        const double* lxxt = a.lxx + ((size_t)tr * a.T + t) * NN;
+        const double* luxt = a.lux ? a.lux + ((size_t)tr * S + t) * NM : nullptr;
+        const double* luut = a.luu + ((size_t)tr * S + t) * MM;
+        const double* lxt = a.lx + ((size_t)tr * a.T + t) * N;
+        const double* lut = a.lu + ((size_t)tr * S + t) * M;
+#pragma unroll
+        for (int q = 0; q < E_NN; ++q) {
+            const int e = lane + q * NL;
+            if (NN % NL == 0 || e < NN) {
+                const int i = e / N, j = e % N;
+                // rows 0..NQ−1 of fx are [0 I]; the load below always uses a valid offset of the packed row (top rows read element 0)
+                const int off = (i < NQ) ? 0 : ((j < NQ) ? j * NQ + (i - NQ) : NQ * NQ + (j - NQ) * NQ + (i - NQ));
+                const double v = d1[off];
+                f.a[q] = (i < NQ) ? ((j == i + NQ) ? 1.0 : 0.0) : v;
+                f.lxx[q] = lxxt[e];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < E_NM; ++q) {
+            const int e = lane + q * NL;
+            if (NM % NL == 0 || e < NM) {
+                const int i = e / M, j = e % M;                     // fu is n×m row-major; lux is m×n row-major (same count)
+                const double v = du[(i < NQ) ? 0 : j * NQ + (i - NQ)];
+                f.b[q] = (i < NQ) ? 0.0 : v;
+                f.lux[q] = luxt ? luxt[e] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < E_MM; ++q) { const int e = lane + q * NL; if (MM % NL == 0 || e < MM) f.luu[q] = luut[e]; }
+#pragma unroll
+        for (int q = 0; q < E_N; ++q) { const int e = lane + q * NL; if (N % NL == 0 || e < N) f.lx[q] = lxt[e]; }
+#pragma unroll
+        for (int q = 0; q < E_M; ++q) { const int e = lane + q * NL; if (M % NL == 0 || e < M) f.lu[q] = lut[e]; }
+    }
+
+    OD_HD static void run(const RiccatiArgs& a, const int tr, double* ws, const int lane) {
+        const int T = a.T, S = T - 1;
+        double* P = ws + O_P0; double* Pn = ws + O_P1; double* p = ws + O_p0; double* pn = ws + O_p1;
+        double* A = ws + O_A; double* PA = ws + O_PA; double* Qxx = ws + O_QXX; double* Bm = ws + O_B; double* PB = ws + O_PB;
+        double* Qux = ws + O_QUX; double* Kt = ws + O_K; double* QK = ws + O_QK; double* Quu = ws + O_QUU;
+        double* Qx = ws + O_QX; double* Qu = ws + O_QU; double* kt = ws + O_k; double* Qk = ws + O_Qk;
+        {
+            const double* lxT = a.lx + ((size_t)tr * T + S) * N;
+            const double* lxxT = a.lxx + ((size_t)tr * T + S) * NN;
+            for (int e = lane; e < NN; e += NL) P[e] = lxxT[e];
+            for (int e = lane; e < N; e += NL) p[e] = lxT[e];
+        }
+        double dv1 = 0.0, dv2 = 0.0;
+        int bad = 0;
+        Fetch cur, nxt;
+        fetch(a, tr, S - 1, lane, cur);
+        for (int t = S - 1; t >= 0; --t) {
+            if (t > 0) fetch(a, tr, t - 1, lane, nxt);               // in flight during this step
+#pragma unroll
+            for (int q = 0; q < E_NN; ++q) { const int e = lane + q * NL; if (NN % NL == 0 || e < NN) A[e] = cur.a[q]; }
+#pragma unroll
+            for (int q = 0; q < E_NM; ++q) { const int e = lane + q * NL; if (NM % NL == 0 || e < NM) Bm[e] = cur.b[q]; }
+            riccati_sync();                                          // A, B, and the P / p of the previous step are visible
+#pragma unroll
+            for (int q = 0; q < E_NN; ++q) {
+                const int e = lane + q * NL;
+                if (NN % NL == 0 || e < NN) { const int i = e / N, j = e % N; double s = 0.0;
+#pragma unroll
+                    for (int l = 0; l < N; ++l) s += P[i * N + l] * A[l * N + j];
+                    PA[e] = s; }
+            }
+#pragma unroll
+            for (int q = 0; q < E_NM; ++q) {
+                const int e = lane + q * NL;
+                if (NM % NL == 0 || e < NM) { const int i = e / M, j = e % M; double s = 0.0;
+#pragma unroll
+                    for (int l = 0; l < N; ++l) s += P[i * N + l] * Bm[l * M + j];
+                    PB[e] = s; }
+            }
+            riccati_sync();
+#pragma unroll
+            for (int q = 0; q < E_NN; ++q) {
+                const int e = lane + q * NL;
+                if (NN % NL == 0 || e < NN) { const int i = e / N, j = e % N; double s = cur.lxx[q];
+#pragma unroll
+                    for (int l = 0; l < N; ++l) s += A[l * N + i] * PA[l * N + j];
+                    Qxx[e] = s; }
+            }
+#pragma unroll
+            for (int q = 0; q < E_NM; ++q) {
+                const int e = lane + q * NL;
+                if (NM % NL == 0 || e < NM) { const int i = e / N, j = e % N; double s = cur.lux[q];
+#pragma unroll
+                    for (int l = 0; l < N; ++l) s += Bm[l * M + i] * PA[l * N + j];
+                    Qux[e] = s; }
+            }
+#pragma unroll
+            for (int q = 0; q < E_MM; ++q) {
+                const int e = lane + q * NL;
+                if (MM % NL == 0 || e < MM) { const int i = e / M, j = e % M; double s = cur.luu[q] + (i == j ? a.reg : 0.0);
+#pragma unroll
+                    for (int l = 0; l < N; ++l) s += Bm[l * M + i] * PB[l * M + j];
+                    Quu[e] = s; }
+            }
+#pragma unroll
+            for (int q = 0; q < E_N; ++q) {
+                const int e = lane + q * NL;
+                if (N % NL == 0 || e < N) { double s = cur.lx[q];
+#pragma unroll
+                    for (int l = 0; l < N; ++l) s += A[l * N + e] * p[l];
+                    Qx[e] = s; }
+            }
+#pragma unroll
+            for (int q = 0; q < E_M; ++q) {
+                const int e = lane + q * NL;
+                if (M % NL == 0 || e < M) { double s = cur.lu[q];
+#pragma unroll
+                    for (int l = 0; l < N; ++l) s += Bm[l * M + e] * p[l];
+                    Qu[e] = s; }
+            }
+            riccati_sync();
+            // Cholesky of Quu redundantly in every thread; thread c then solves column c of −[Qux | Qu] and forms Quu·(that column)
+            double Lr[MM], Qm[MM];
+            bool pd = true;
+#pragma unroll
+            for (int e = 0; e < MM; ++e) Qm[e] = Quu[e];
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+#pragma unroll
+                for (int j = 0; j <= i; ++j) {
+                    double s = Qm[i * M + j];
+#pragma unroll
+                    for (int l = 0; l < j; ++l) s -= Lr[i * M + l] * Lr[j * M + l];
+                    if (i == j) { pd = pd && (s > 0.0); Lr[i * M + i] = 1.0 / sqrt(s); }      // reciprocal of the diagonal
+                    else Lr[i * M + j] = s * Lr[j * M + j];
+                }
+            }
+            if (!pd) bad = 1;
+            for (int c = lane; c < N + 1; c += NL) {
+                double y[M];
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+                    double s = -((c < N) ? Qux[i * N + c] : Qu[i]);
+#pragma unroll
+                    for (int l = 0; l < i; ++l) s -= Lr[i * M + l] * y[l];
+                    y[i] = s * Lr[i * M + i];
+                }
+#pragma unroll
+                for (int i = M - 1; i >= 0; --i) {
+                    double s = y[i];
+#pragma unroll
+                    for (int l = i + 1; l < M; ++l) s -= Lr[l * M + i] * y[l];
+                    y[i] = s * Lr[i * M + i];
+                }
+#pragma unroll
+                for (int i = 0; i < M; ++i) y[i] = pd ? y[i] : 0.0;
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int l = 0; l < M; ++l) s += Qm[i * M + l] * y[l];
+                    if (c < N) { Kt[i * N + c] = y[i]; QK[i * N + c] = s; } else { kt[i] = y[i]; Qk[i] = s; }
+                }
+            }
+            riccati_sync();
+#pragma unroll
+            for (int q = 0; q < E_NN; ++q) {
+                const int e = lane + q * NL;
+                if (NN % NL == 0 || e < NN) { const int i = e / N, j = e % N; double s = Qxx[e];
+#pragma unroll
+                    for (int l = 0; l < M; ++l) s += Kt[l * N + i] * QK[l * N + j] + Kt[l * N + i] * Qux[l * N + j] + Qux[l * N + i] * Kt[l * N + j];
+                    Pn[e] = s; }
+            }
+#pragma unroll
+            for (int q = 0; q < E_N; ++q) {
+                const int e = lane + q * NL;
+                if (N % NL == 0 || e < N) { double s = Qx[e];
+#pragma unroll
+                    for (int l = 0; l < M; ++l) s += Kt[l * N + e] * Qk[l] + Kt[l * N + e] * Qu[l] + Qux[l * N + e] * kt[l];
+                    pn[e] = s; }
+            }
+            double* Ko = a.K + ((size_t)tr * S + t) * NM;
+            double* ko = a.k + ((size_t)tr * S + t) * M;
+            for (int e = lane; e < NM; e += NL) Ko[e] = Kt[e];
+            for (int e = lane; e < M; e += NL) ko[e] = kt[e];
+#pragma unroll
+            for (int l = 0; l < M; ++l) { dv1 += kt[l] * Qu[l]; dv2 += 0.5 * kt[l] * Qk[l]; }
+            { double* tmp = P; P = Pn; Pn = tmp; tmp = p; p = pn; pn = tmp; }      // (the sync at the top of the next step publishes them)
+            cur = nxt;
+        }
+        if (lane == 0) {
+            if (a.dV) { a.dV[2 * (size_t)tr] = dv1; a.dV[2 * (size_t)tr + 1] = dv2; }
+            if (a.status) a.status[tr] = bad;
+        }
+    }
+};
+
+template <int NQ, int NU, int WARPS>
 __global__ void __launch_bounds__(32 * WARPS) riccati_kernel(const RiccatiArgs a) {
     extern __shared__ __align__(16) double od_smem[];
     const int w = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int tr = blockIdx.x * WARPS + w;
-    if (tr >= a.NT) return;                                   // whole warps only: no partial-warp divergence around __syncwarp
-    riccati_one(a, tr, od_smem + (size_t)w * riccati_ws(2 * a.nq, a.nu), lane, 32);
+    if (tr >= a.NT) return;                                   // whole warps leave together: no divergence around __syncwarp
+    Riccati<NQ, NU, 32>::run(a, tr, od_smem + (size_t)w * Riccati<NQ, NU, 32>::WS, lane);
 }
 
 }  // namespace od

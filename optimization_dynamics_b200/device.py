@@ -84,6 +84,50 @@ class DeviceStepper:
         return all_gather_rows(out_local, B_total, gathered), status
 
 
+class DeviceSolverStages:
+    """The two stages either side of the derivative sweep, on torch CUDA tensors and torch's current stream (asynchronous):
+    `backward_pass` (od_riccati_batch_device) and `rollouts` (od_rollout_batch_device).  With DeviceStepper.step_grad_packed in
+    between, one iLQR iteration for NT trajectories is three launches with no host round trip."""
+
+    def __init__(self, stepper: DeviceStepper):
+        self.stepper = stepper
+        self.torch = stepper.torch
+        self.nq, self.nu = stepper.nq, stepper.nu
+
+    def _p(self, t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def backward_pass(self, jac, lx, lu, lxx, luu, lux=None, reg=0.0, K=None, k=None, dV=None, status=None):
+        t = self.torch
+        NT, S = jac.shape[0], jac.shape[1]
+        n, m = 2 * self.nq, self.nu
+        for a in (jac, lx, lu, lxx, luu) + (() if lux is None else (lux,)):
+            assert a.is_cuda and a.dtype == t.float64 and a.is_contiguous()
+        K = t.empty((NT, S, m, n), dtype=t.float64, device=jac.device) if K is None else K
+        k = t.empty((NT, S, m), dtype=t.float64, device=jac.device) if k is None else k
+        dV = t.empty((NT, 2), dtype=t.float64, device=jac.device) if dV is None else dV
+        status = t.empty((NT,), dtype=t.int32, device=jac.device) if status is None else status
+        self.stepper._bind_stream()
+        _lib.check(_lib.lib().od_riccati_batch_device(self.stepper.dyn._handle(), NT, S + 1, self._p(jac), self._p(lx), self._p(lu), self._p(lxx),
+                                                      self._p(luu), self._p(lux), float(reg), self._p(K), self._p(k), self._p(dV), self._p(status)))
+        return K, k, dV, status
+
+    def rollouts(self, x1, ubar, xbar=None, K=None, k=None, alpha=None, X=None, U=None, status=None):
+        """x1 [R, 2nq]; ubar [T-1, nu] (shared) or [R, T-1, nu]; xbar [T, 2nq], K [T-1, nu, 2nq], k [T-1, nu], alpha [R]."""
+        t = self.torch
+        R = x1.shape[0]
+        per = ubar.dim() == 3
+        S = ubar.shape[-2]
+        n, m = 2 * self.nq, self.nu
+        X = t.empty((R, S + 1, n), dtype=t.float64, device=x1.device) if X is None else X
+        U = t.empty((R, S, m), dtype=t.float64, device=x1.device) if U is None else U
+        status = t.empty((R, S), dtype=t.int32, device=x1.device) if status is None else status
+        self.stepper._bind_stream()
+        _lib.check(_lib.lib().od_rollout_batch_device(self.stepper.dyn._handle(), R, S + 1, self._p(x1), self._p(ubar), S * m if per else 0, self._p(xbar),
+                                                      self._p(K), self._p(k), self._p(alpha), self._p(X), self._p(U), self._p(status), None))
+        return X, U, status
+
+
 class FusedGather:
     """All-gather fused into the step kernel over NVLink peer memory (torch symmetric memory supplies the peer-mapped buffers).
 

@@ -67,10 +67,12 @@ extern "C" int hc_contact_rollout(int model, int R, int T, const double* x1, con
 extern "C" int hc_riccati(int NT, int T, int nq, int nu, const double* jac, const double* lx, const double* lu, const double* lxx, const double* luu,
                           const double* lux, double reg, double* K, double* k, double* dV, int* status) {
     RiccatiArgs a; memset(&a, 0, sizeof(a));
-    a.NT = NT; a.T = T; a.nq = nq; a.nu = nu; a.jac = jac; a.lx = lx; a.lu = lu; a.lxx = lxx; a.luu = luu; a.lux = lux; a.reg = reg;
+    a.NT = NT; a.T = T; a.jac = jac; a.lx = lx; a.lu = lu; a.lxx = lxx; a.luu = luu; a.lux = lux; a.reg = reg;
     a.K = K; a.k = k; a.dV = dV; a.status = status;
-    std::vector<double> ws(riccati_ws(2 * nq, nu));
-    for (int tr = 0; tr < NT; ++tr) riccati_one(a, tr, ws.data(), 0, 1);
+    if (nq == 4 && nu == 2) { std::vector<double> ws(Riccati<4, 2, 1>::WS); for (int tr = 0; tr < NT; ++tr) Riccati<4, 2, 1>::run(a, tr, ws.data(), 0); }
+    else if (nq == 2 && nu == 1) { std::vector<double> ws(Riccati<2, 1, 1>::WS); for (int tr = 0; tr < NT; ++tr) Riccati<2, 1, 1>::run(a, tr, ws.data(), 0); }
+    else if (nq == 5 && nu == 2) { std::vector<double> ws(Riccati<5, 2, 1>::WS); for (int tr = 0; tr < NT; ++tr) Riccati<5, 2, 1>::run(a, tr, ws.data(), 0); }
+    else return 1;
     return 0;
 }
 
