@@ -113,6 +113,35 @@ function step_grad_batch(model::ImplicitDynamics, X::Matrix{Float64}, U::Matrix{
     return q3, dq1, dq2, du1, status
 end
 
+# rollout(model, x1, ū) — iLQR.rollout (examples/cartpole.jl:79): T−1 sequential calls of f in ONE launch.  ū is nu×(T−1).
+# With a policy (x̄ 2nq×T, K as a vector of nu×2nq matrices, k nu×(T−1)) and step sizes α it is IterativeLQR's forward pass for all
+# line-search candidates at once: u[t] = ū[t] + α k[t] + K[t](x[t] − x̄[t]).  Returns X (2nq×T×R), U (nu×(T−1)×R), status ((T−1)×R).
+function rollout_batch(model::ImplicitDynamics, x1::Matrix{Float64}, ū::Matrix{Float64};
+                       x̄=nothing, K=nothing, k=nothing, α=nothing)
+    R = size(x1, 2); S = size(ū, 2); T = S + 1; nx = 2 * model.nq; nu = model.nu
+    X = zeros(nx, T, R); U = zeros(nu, S, R); status = zeros(Int32, S, R)
+    Kc = K === nothing ? C_NULL : permutedims(cat(K...; dims=3), (2, 1, 3))      # [t][control][state] row-major = state-fastest
+    check(ccall((:od_rollout_batch, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Int32}),
+                model.handle, R, T, x1, ū, 0, x̄ === nothing ? C_NULL : x̄, Kc, k === nothing ? C_NULL : k, α === nothing ? C_NULL : α, X, U, status))
+    return X, U, status
+end
+rollout(model::ImplicitDynamics, x1::Vector{Float64}, ū::Vector{Vector{Float64}}) =
+    (X = rollout_batch(model, reshape(x1, :, 1), reduce(hcat, ū))[1]; [X[:, t, 1] for t = 1:size(X, 2)])
+
+# backward_pass_batch — IterativeLQR's Riccati recursion for NT trajectories at once, on the packed rows of the derivative sweep
+# (jac: (nq + nq(2nq+nu))×(T−1)×NT).  lx n×T×NT, lu m×(T−1)×NT, lxx n×n×T×NT, luu m×m×(T−1)×NT (symmetric, so Julia's column-major
+# blocks are the row-major blocks the ABI expects), lux optional as n×m×(T−1)×NT (= row-major m×n).  Returns K (n×m×(T−1)×NT, i.e.
+# K[:, :, t, a]' is the nu×2nq gain), k (m×(T−1)×NT), ΔV (2×NT), status.
+function backward_pass_batch(model::ImplicitDynamics, jac, lx, lu, lxx, luu; lux=nothing, reg=0.0)
+    NT = size(jac, 3); S = size(jac, 2); n = 2 * model.nq; m = model.nu
+    K = zeros(n, m, S, NT); k = zeros(m, S, NT); ΔV = zeros(2, NT); status = zeros(Int32, NT)
+    check(ccall((:od_riccati_batch, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Int32}),
+                model.handle, NT, S + 1, jac, lx, lu, lxx, luu, lux === nothing ? C_NULL : lux, reg, K, k, ΔV, status))
+    return K, k, ΔV, status
+end
+
 # state_to_configuration — src/dynamics.jl:131-145
 function state_to_configuration(x::Vector{Vector{T}}) where T
     nq = convert(Int, floor(length(x[1]) / 2))
@@ -196,6 +225,6 @@ function soc_projection_gradient(x, info::RocketInfo)
     return dup
 end
 
-export ImplicitDynamics, f, fx, fu, step_grad_batch, state_to_configuration, GradientBundle, gradient!, fx_gb, fu_gb,
+export ImplicitDynamics, f, fx, fu, step_grad_batch, rollout, rollout_batch, backward_pass_batch, state_to_configuration, GradientBundle, gradient!, fx_gb, fu_gb,
        RocketInfo, f_rocket, fx_rocket, fu_rocket, f_rocket_proj, fx_rocket_proj, fu_rocket_proj, soc_projection, soc_projection_gradient
 end # module
