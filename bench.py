@@ -169,9 +169,11 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extra", action="store_true", help="also report a saturating batch (262144 per GPU) in the JSON line")
-    ap.add_argument("--collective", default="fused", choices=["fused", "nccl"],
-                    help="N>1: 'fused' = all-gather fused into the kernel over NVLink peer memory (falls back to nccl if symmetric memory "
-                         "is unavailable); 'nccl' = kernel + ncclAllGather")
+    ap.add_argument("--collective", default="fused", choices=["fused", "fused-kernel-barrier", "fused-launch-barrier", "nccl"],
+                    help="N>1: 'fused' = all-gather fused into the kernel over NVLink peer memory, cross-rank barrier fused as well up to 4 ranks "
+                         "(falls back to nccl if symmetric memory is unavailable); 'fused-kernel-barrier' / 'fused-launch-barrier' force the "
+                         "barrier variant; "
+                         "'nccl' = kernel + ncclAllGather")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 200 and args.warmup == 10:
@@ -210,10 +212,10 @@ def main():
     gathered = torch.empty((B_total, stepper.out_width), dtype=torch.float64, device=dev) if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # 2× the 126 MB L2
     fused = None
-    if world > 1 and args.collective == "fused":
+    if world > 1 and args.collective != "nccl":
         okf = torch.ones(1, device=dev)
         try:
-            fused = FusedGather(stepper, B_total)
+            fused = FusedGather(stepper, B_total, sync={"fused": "auto", "fused-kernel-barrier": "kernel", "fused-launch-barrier": "launch"}[args.collective])
         except Exception as ex:                       # symmetric memory unavailable: every rank must take the same path
             sys.stderr.write("rank %d: fused gather unavailable (%r), using ncclAllGather\n" % (rank, ex))
             okf.zero_()
@@ -330,7 +332,9 @@ def main():
                                    "kappa_eval=1e-4, kappa_grad=1e-3, r_tol=1e-8 (BASELINE.json configs[3])" % B,
                        "batch_per_gpu": B, "global_batch": B_total, "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
                        "collective": ("none (1 GPU)" if world == 1 else
-                                      "all-gather fused into the kernel: P2P stores of each finished 352-B row into every rank's buffer over NVLink + symmetric-memory barrier"
+                                      ("all-gather and cross-rank barrier fused into the kernel: P2P stores of each finished 352-B row into every rank's buffer over NVLink, "
+                                       "completion flags published by the last block of each rank" if fused.sync == "kernel" else
+                                       "all-gather fused into the kernel: P2P stores of each finished 352-B row into every rank's buffer over NVLink + symmetric-memory barrier launch")
                                       if fused is not None else "kernel + ncclAllGather of 352-B rows"),
                        "gather_check_bitwise_equal_to_nccl": gather_check, "converged_fraction": ok_frac},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),

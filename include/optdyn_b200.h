@@ -90,6 +90,15 @@ int od_step_grad_packed_device(od_handle* hd, int B, const double* in, double* o
  * (the Jacobians the sequential Riccati pass needs). */
 int od_step_grad_packed_gather_device(od_handle* hd, int B, const double* in, long long row0, int world, int rank,
                                       const uint64_t* gather_buffers, int32_t* status, int32_t* iters);
+/* Same, with the cross-rank barrier fused into the kernel as well: flag_buffers[r] = rank r's flag array (world × uint64, zeroed
+ * once, peer-mapped like the gather buffers), block_counter = a zeroed uint32 in this rank's device memory, epoch = 1, 2, 3, …
+ * (the same value on every rank for the same step).  The last block of each rank to finish publishes `epoch` to every peer and
+ * waits for every peer's, so when the kernel has completed on this rank's stream all rows of all ranks are in this rank's buffer:
+ * no separate barrier launch.  Alternate two gather buffers between consecutive steps if a consumer of step k may still be
+ * reading when step k+1 starts on a faster rank.  Register-path models only (hopper, cartpole, acrobot). */
+int od_step_grad_packed_gather_sync_device(od_handle* hd, int B, const double* in, long long row0, int world, int rank,
+                                           const uint64_t* gather_buffers, const uint64_t* flag_buffers, uint32_t* block_counter,
+                                           uint64_t epoch, int32_t* status, int32_t* iters);
 
 /* Batched closed-loop rollouts — the caller of f in the outer solver: iLQR.rollout(model, x1, ū) (reference examples/cartpole.jl:79,
  * acrobot.jl:92, planar_push.jl:113, hopper.jl:272) and the forward pass / Armijo line search of IterativeLQR (step sizes down to

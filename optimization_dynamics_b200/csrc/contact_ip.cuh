@@ -795,6 +795,15 @@ struct StepArgs {
     int n_peers, self_rank;
     long long gather_row0; int gather_width;
     double* peer_out[8];
+    // Packed output (q3/dq1/dq2/du point into one row of width NOUT, 16-byte aligned): the register path stores it as 16-byte pairs.
+    int packed_out;
+    // Cross-GPU barrier fused into the kernel (replaces the separate barrier launch after the fused all-gather): every thread
+    // fences its peer stores, the last block of the grid to finish publishes `sync_epoch` into slot `self_rank` of every peer's
+    // flag array and waits until every peer has published it here.  sync_flags[r] = rank r's flag array (world × u64) as mapped
+    // in this process; sync_counter = this rank's block counter (device memory, zero before the first launch).  Null = off.
+    unsigned long long* sync_flags[8];
+    unsigned int* sync_counter;
+    unsigned long long sync_epoch;
     SolverOpts opts;
 };
 
@@ -923,6 +932,25 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
         double* o1 = grad ? a.dq1 + (size_t)i * a.out_stride_dq - NQ : nullptr;
         double* o2 = grad ? a.dq2 + (size_t)i * a.out_stride_dq - (NQ + NQQ) : nullptr;
         double* o3 = grad ? a.du + (size_t)i * a.out_stride_du - (NQ + 2 * NQQ) : nullptr;
+        if (a.packed_out && grad && oq && NOUT % 2 == 0) {
+            // whole row contiguous and 16-byte aligned: consecutive lanes store consecutive 16-byte pairs (128 B per 8 lanes)
+            const double2* src = reinterpret_cast<const double2*>(ws);
+            double2* dst = reinterpret_cast<double2*>(oq);
+#pragma unroll
+            for (int t = 0; t < (NOUT / 2 + G - 1) / G; ++t) {
+                const int e = g + G * t;
+                if (G == 1 || e < NOUT / 2) {
+                    const double2 v = src[e];
+                    dst[e] = v;
+#ifdef __CUDA_ARCH__
+                    if (a.n_peers > 1) {
+                        const size_t off = ((size_t)(a.gather_row0 + i) * a.gather_width) / 2 + e;
+                        for (int p = 0; p < a.n_peers; ++p) if (p != a.self_rank) reinterpret_cast<double2*>(a.peer_out[p])[off] = v;
+                    }
+#endif
+                }
+            }
+        } else {
 #pragma unroll
         for (int t = 0; t < (NOUT + G - 1) / G; ++t) {
             const int e = g + G * t;
@@ -939,6 +967,7 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
 #endif
                 }
             }
+        }
         }
     } else {
         if (a.want_grad && a.dq1) {
@@ -981,6 +1010,24 @@ __global__ void __launch_bounds__(G * PPB) contact_step_kernel(const StepArgs a)
     int i = blockIdx.x * PPB + slot;
     if (i >= a.B) i = a.B - 1;               // padding lanes of the last warp repeat the last problem (identical values, same addresses)
     contact_step_one<M, G, PPB, REG>(a, i, od_smem + slot * ContactIP<M, G, PPB, REG>::WS_SLOT, g, 0xffffffffu);
+    if (a.sync_counter) {                                   // fused cross-GPU barrier (see StepArgs)
+        __threadfence_system();                             // this thread's peer stores are performed before the block is counted
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned prev = atomicAdd(a.sync_counter, 1u);
+            if (prev == gridDim.x - 1) {                    // last block of this rank: every row of the shard is on its way / there
+                *a.sync_counter = 0u;                       // ready for the next launch (stream-ordered)
+                __threadfence_system();
+                for (int p = 0; p < a.n_peers; ++p)
+                    if (p != a.self_rank) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.sync_flags[p] + a.self_rank), "l"(a.sync_epoch) : "memory");
+                for (int p = 0; p < a.n_peers; ++p) {
+                    if (p == a.self_rank) continue;
+                    unsigned long long v;
+                    do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.sync_flags[a.self_rank] + p) : "memory"); } while (v < a.sync_epoch);
+                }
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1023,6 +1070,7 @@ OD_HD void contact_rollout_one(const RolloutArgs& ra, const int r, double* ws, c
     for (int k = 0; k < 4; ++k) a.fric[k] = ra.fric[k];
     a.want_eval = 1; a.want_grad = 0; a.eta = nullptr; a.n_eta = 0;
     a.n_peers = 0; a.self_rank = 0; a.gather_row0 = 0; a.gather_width = 0;
+    a.packed_out = 0; a.sync_counter = nullptr; a.sync_epoch = 0;
     a.opts = ra.opts;
     const double alpha = ra.alpha ? ra.alpha[r] : 1.0;
     const double* ub = ra.ubar + (size_t)r * ra.ubar_stride;

@@ -233,6 +233,13 @@ static cudaError_t launch_rollout(const RolloutArgs& a, cudaStream_t s) {
     return launch_rollout_cfg<M, 4, 8, false>(a, s);
 }
 
+// Zero-copy output needs whole rows leaving the kernel as contiguous stores (the register path stages the packed row in shared
+// memory); the shared-memory-LU path scatters 8-byte stores, which PCIe handles badly (measured: 2.4x slower end to end).
+static bool rows_leave_coalesced(int model, int B) {
+    const bool regok = model == OD_HOPPER || model == OD_CARTPOLE_FRICTION || model == OD_ACROBOT_IMPACT;
+    return regok && reg_path() && lanes_for(B) >= 4;
+}
+
 static int launch_step(od_handle* hd, StepArgs& a) {
     if (a.B <= 0) return 0;
     a.h = hd->h;
@@ -280,6 +287,7 @@ int od_step_grad_packed_device(od_handle* hd, int B, const double* in, double* o
     a.q3 = out; a.dq1 = want_grad ? out + d.nq : nullptr; a.dq2 = out + d.nq + d.nq * d.nq; a.du = out + d.nq + 2 * d.nq * d.nq;
     a.out_stride_q3 = outw; a.out_stride_dq = outw; a.out_stride_du = outw;
     a.status = status; a.iters = iters; a.want_eval = want_eval; a.want_grad = want_grad;
+    a.packed_out = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
     return launch_step(hd, a);
 }
 
@@ -298,6 +306,33 @@ int od_step_grad_packed_gather_device(od_handle* hd, int B, const double* in, lo
     a.status = status; a.iters = iters; a.want_eval = 1; a.want_grad = 1;
     a.n_peers = world; a.self_rank = rank; a.gather_row0 = row0; a.gather_width = outw;
     for (int r = 0; r < world; ++r) a.peer_out[r] = (double*)gather_buffers[r];
+    bool aligned = true;
+    for (int r = 0; r < world; ++r) aligned = aligned && ((gather_buffers[r] & 15) == 0);
+    a.packed_out = aligned ? 1 : 0;
+    return launch_step(hd, a);
+}
+
+int od_step_grad_packed_gather_sync_device(od_handle* hd, int B, const double* in, long long row0, int world, int rank,
+                                           const uint64_t* gather_buffers, const uint64_t* flag_buffers, uint32_t* block_counter,
+                                           uint64_t epoch, int32_t* status, int32_t* iters) {
+    if (!hd) return fail("null handle");
+    if (world < 1 || world > 8 || rank < 0 || rank >= world || !gather_buffers || !flag_buffers || !block_counter || epoch == 0)
+        return fail("od_step_grad_packed_gather_sync_device: need 1 <= world <= 8, the peer buffer and flag tables, a block counter and epoch >= 1");
+    if (!rows_leave_coalesced(hd->model, B)) return fail("od_step_grad_packed_gather_sync_device: needs the cooperative-lane register path (hopper, cartpole, acrobot)");
+    Dims d; dims_of(hd->model, &d);
+    OD_CUDA(cudaSetDevice(hd->device));
+    const int inw = 2 * d.nq + d.nu, outw = d.nq + d.nq * inw;
+    double* out = (double*)gather_buffers[rank] + (size_t)row0 * outw;
+    StepArgs a; memset(&a, 0, sizeof(a));
+    a.B = B; a.q1 = in; a.q2 = in + d.nq; a.u = in + 2 * d.nq; a.in_stride_q = inw; a.in_stride_u = inw;
+    a.q3 = out; a.dq1 = out + d.nq; a.dq2 = out + d.nq + d.nq * d.nq; a.du = out + d.nq + 2 * d.nq * d.nq;
+    a.out_stride_q3 = outw; a.out_stride_dq = outw; a.out_stride_du = outw;
+    a.status = status; a.iters = iters; a.want_eval = 1; a.want_grad = 1;
+    a.n_peers = world; a.self_rank = rank; a.gather_row0 = row0; a.gather_width = outw;
+    bool aligned = true;
+    for (int r = 0; r < world; ++r) { a.peer_out[r] = (double*)gather_buffers[r]; a.sync_flags[r] = (unsigned long long*)flag_buffers[r]; aligned = aligned && ((gather_buffers[r] & 15) == 0); }
+    a.packed_out = aligned ? 1 : 0;
+    a.sync_counter = block_counter; a.sync_epoch = epoch;
     return launch_step(hd, a);
 }
 
@@ -318,13 +353,6 @@ static int zero_copy_mode() {
     if (v < 0) { const char* e = getenv("OD_ZEROCOPY"); v = e ? atoi(e) : 1; }
     return v;
 }
-// Zero-copy output needs whole rows leaving the kernel as contiguous stores (the register path stages the packed row in shared
-// memory); the shared-memory-LU path scatters 8-byte stores, which PCIe handles badly (measured: 2.4x slower end to end).
-static bool rows_leave_coalesced(int model, int B) {
-    const bool regok = model == OD_HOPPER || model == OD_CARTPOLE_FRICTION || model == OD_ACROBOT_IMPACT;
-    return regok && reg_path() && lanes_for(B) >= 4;
-}
-
 // Host-buffer entry point.  When the caller's buffers are pinned host memory (cudaHostAlloc / cudaHostRegister — what a Julia
 // or Python host uses for its trajectory arrays), the kernel reads the 80-B input rows and writes each finished 352-B output row
 // straight over PCIe: the device→host transfer of a row overlaps the problems that are still iterating, and the separate
