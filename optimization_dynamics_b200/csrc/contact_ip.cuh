@@ -109,8 +109,11 @@ struct ContactIP {
     static constexpr int OFF_ZS = OFF_CP + (M::ROBUST_IFT ? NR : 0);   // snapshot of the iterate at which the IFT is taken
     // REG workspace (contiguous per problem): staging rows [NR][PW] (K | carried right-hand sides; reused for the packed output
     // row), iterate snapshot, q3.  Even pitch and offsets: rows are moved as 16-byte pairs; WS/2 odd spreads problems over banks.
+    // Models with the rank-revealing IFT run it (once per problem) in the shared-memory-LU layout at the start of the same
+    // workspace, so the snapshot / q3 slots sit behind both areas.
     static constexpr int PW = ((NR + NTP + 1) / 2) * 2;
-    static constexpr int ROFF_ZS = NR * PW;
+    static constexpr int ROBUST_END = M::ROBUST_IFT ? OFF_CP + NR : 0;
+    static constexpr int ROFF_ZS = ((((NR * PW > ROBUST_END) ? NR * PW : ROBUST_END) + 1) / 2) * 2;
     static constexpr int ROFF_Q3 = ROFF_ZS + NZ;
     static constexpr int RWS0 = ((ROFF_Q3 + NQ + 1) / 2) * 2;
     static constexpr int RWS = ((RWS0 / 2) % 2 == 1) ? RWS0 : RWS0 + 2;
@@ -135,10 +138,10 @@ struct ContactIP {
         double a[REG ? RPL : 1][REG ? NR + 1 : 1];   // REG: this lane's rows of the eliminated [K | affine rhs]
         int piv[REG ? NR : 1];                       // REG: pivot row of every elimination step
         OD_HD double& S(int r, int j) const { return ws[r * PW + j]; }     // REG staging area
-        OD_HD double& K(int i, int j) const { return ws[(i * NRP + j) * PPB]; }
-        OD_HD double& X(int v, int i) const { return ws[(OFF_X + v * NRP + i) * PPB]; }
-        OD_HD double& PIV(int i) const { return ws[(OFF_PIV + i) * PPB]; }
-        OD_HD double& CP(int i) const { return ws[(OFF_CP + i) * PPB]; }
+        OD_HD double& K(int i, int j) const { return ws[(i * NRP + j) * WS_STRIDE]; }
+        OD_HD double& X(int v, int i) const { return ws[(OFF_X + v * NRP + i) * WS_STRIDE]; }
+        OD_HD double& PIV(int i) const { return ws[(OFF_PIV + i) * WS_STRIDE]; }
+        OD_HD double& CP(int i) const { return ws[(OFF_CP + i) * WS_STRIDE]; }
         OD_HD void sync() const {
 #ifdef __CUDA_ARCH__
             if (G > 1) __syncwarp(gmask);
@@ -279,7 +282,7 @@ struct ContactIP {
     }
     // every lane of the group writes the same values (benign); factor() synchronises before reading
     OD_HD static void assemble(const Z& z, const double* th, const double* trc, const double* trv, Lin& L) {
-        static_assert(NTP >= G, "each lane needs a private scratch vector");
+        static_assert(REG || NTP >= G, "each lane needs a private scratch vector");
         double D[NQ * NQ], Eg[NQ * NC1], Eb[NQ * NB1];
         M::jac(z.q, z.gam, z.b, th, trc, trv, D, Eg, Eb, L.N, L.V, L.Mpsi);
         L.sync();                                             // no lane may still be reading the previous factorisation
@@ -915,11 +918,20 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
     // ---- IFT at the snapshot.  It sits after the loop on purpose: the problems of a warp converge at different iterations, and a
     // sensitivity pass inside the loop would be executed once per distinct convergence iteration (up to 8× per warp).
     if constexpr (REG) {
-        const bool grad = a.want_grad && a.dq1;
+        bool grad = a.want_grad && a.dq1;
         if (grad) {
             IP::load_z(L, z);
             M::trig_var(z.q, th, trv);
-            if (!IP::sensitivities_reg(L, z, th, trc, trv)) st_g = ST_FAIL;
+            if constexpr (M::ROBUST_IFT) {
+                // rank-revealing factorisation in the shared-memory-LU layout; it writes the Jacobian blocks to their destination
+                // itself, only q3 goes through the staged row below
+                IP::assemble(z, th, trc, trv, L);
+                if (!IP::sensitivities_robust(L, z, th, trc, trv, a.dq1 + (size_t)i * a.out_stride_dq, a.dq2 + (size_t)i * a.out_stride_dq,
+                                              a.du + (size_t)i * a.out_stride_du)) st_g = ST_FAIL;
+                grad = false;
+            } else {
+                if (!IP::sensitivities_reg(L, z, th, trc, trv)) st_g = ST_FAIL;
+            }
         } else {
             L.sync();
         }

@@ -179,10 +179,13 @@ static cudaError_t launch_contact_cfg(const StepArgs& a, cudaStream_t s) {
 // Lanes per problem: 1 = one thread per problem (throughput configuration, large batches; LU in shared memory); 4 / 8 =
 // cooperative groups (latency configuration: a 4096-problem batch alone would put a single warp on each SM) with the
 // register-resident Gauss–Jordan of group_gj.cuh.  OD_LANES overrides the heuristic; OD_REG=0 forces the shared-memory LU.
-static int lanes_for(int B) {
+static int lanes_for(int B, bool heavy = false) {
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("OD_LANES"); forced = e ? atoi(e) : 0; }
     if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16) return forced;
+    // planar push (20×20 reduced system, 35 variables): measured 1024 problems 5.2 / 4.1 / 3.4 ms with 4 / 8 / 16 lanes,
+    // 25 600 problems 12.0 / 10.0 ms with 4 / 8 lanes (register path; shared-memory LU: 5.3 and 12.0 ms)
+    if (heavy) return B <= 4096 ? 16 : 8;
     if (B <= 8192) return 8;       // measured on B200 (hopper): 4096 problems 0.099 ms with 8 lanes, 0.106 with 4, 0.127 with 16, 0.176 with 1
     return 4;                      // 262144 problems: 62 M solves/s with 4 lanes (register path) vs 57 M with 1 lane (shared-memory LU)
 }
@@ -195,7 +198,7 @@ static bool reg_path() {
 // WIDE: models large enough for 8 lanes; REGOK: models whose IFT runs on the register path (not the rank-revealing one)
 template <class M, bool WIDE, bool REGOK>
 static cudaError_t launch_contact(const StepArgs& a, cudaStream_t s) {
-    const int lanes = lanes_for(a.B);
+    const int lanes = lanes_for(a.B, M::ROBUST_IFT);
     if constexpr (REGOK) {
         if (reg_path()) {
             if constexpr (WIDE) { if (lanes == 16) return launch_contact_cfg<M, 16, 2, true>(a, s); }
@@ -223,9 +226,10 @@ static cudaError_t launch_rollout_cfg(const RolloutArgs& a, cudaStream_t s) {
 // rollouts are latency-bound for any realistic count (≤ a few thousand): cooperative lanes, register path where the model has it
 template <class M, bool WIDE, bool REGOK>
 static cudaError_t launch_rollout(const RolloutArgs& a, cudaStream_t s) {
-    const int lanes = lanes_for(a.R);
+    const int lanes = lanes_for(a.R, M::ROBUST_IFT);
     if constexpr (REGOK) {
         if (reg_path()) {
+            if constexpr (WIDE) { if (lanes == 16) return launch_rollout_cfg<M, 16, 2, true>(a, s); }
             if constexpr (WIDE) { if (lanes == 8) return launch_rollout_cfg<M, 8, 4, true>(a, s); }
             return launch_rollout_cfg<M, 4, 8, true>(a, s);
         }
@@ -252,7 +256,7 @@ static int launch_step(od_handle* hd, StepArgs& a) {
         case OD_ACROBOT_NOMINAL: e = launch_contact<AcrobotNominalModel, false, false>(a, hd->stream); break;
         case OD_CARTPOLE_FRICTION: e = launch_contact<CartpoleFrictionModel, false, true>(a, hd->stream); break;
         case OD_CARTPOLE_FRICTIONLESS: e = launch_contact<CartpoleFrictionlessModel, false, false>(a, hd->stream); break;
-        case OD_PLANAR_PUSH: e = launch_contact<PlanarPushModel, true, false>(a, hd->stream); break;
+        case OD_PLANAR_PUSH: e = launch_contact<PlanarPushModel, true, true>(a, hd->stream); break;
         case OD_HOPPER: e = launch_contact<HopperModel, true, true>(a, hd->stream); break;
         default: return fail("this entry point needs a contact model handle (not OD_ROCKET)");
     }
@@ -441,7 +445,7 @@ int od_rollout_batch_device(od_handle* hd, int R, int T, const double* x1, const
         case OD_ACROBOT_NOMINAL: e = launch_rollout<AcrobotNominalModel, false, false>(a, hd->stream); break;
         case OD_CARTPOLE_FRICTION: e = launch_rollout<CartpoleFrictionModel, false, true>(a, hd->stream); break;
         case OD_CARTPOLE_FRICTIONLESS: e = launch_rollout<CartpoleFrictionlessModel, false, false>(a, hd->stream); break;
-        case OD_PLANAR_PUSH: e = launch_rollout<PlanarPushModel, true, false>(a, hd->stream); break;
+        case OD_PLANAR_PUSH: e = launch_rollout<PlanarPushModel, true, true>(a, hd->stream); break;
         case OD_HOPPER: e = launch_rollout<HopperModel, true, true>(a, hd->stream); break;
         default: return fail("od_rollout_batch: bad model");
     }

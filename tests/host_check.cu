@@ -35,7 +35,7 @@ extern "C" int hc_contact_step(int model, int B, const double* q1, const double*
         case 1: run_contact<AcrobotNominalModel>(a, reg); break;
         case 2: run_contact<CartpoleFrictionModel>(a, reg); break;
         case 3: run_contact<CartpoleFrictionlessModel>(a, reg); break;
-        case 4: run_contact<PlanarPushModel>(a, reg && false); break;
+        case 4: run_contact<PlanarPushModel>(a, reg); break;
         case 5: run_contact<HopperModel>(a, reg); break;
         default: return 1;
     }
@@ -57,7 +57,7 @@ extern "C" int hc_contact_rollout(int model, int R, int T, const double* x1, con
     switch (model) {
         case 0: run_rollout<AcrobotImpactModel>(a, reg); break;
         case 2: run_rollout<CartpoleFrictionModel>(a, reg); break;
-        case 4: run_rollout<PlanarPushModel>(a, 0); break;
+        case 4: run_rollout<PlanarPushModel>(a, reg); break;
         case 5: run_rollout<HopperModel>(a, reg); break;
         default: return 1;
     }

@@ -16,7 +16,7 @@ from common import CONFIGS, compare, oracle_pair
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-REG_MODELS = ["hopper", "acrobot_impact", "cartpole_friction"]     # models whose latency configuration uses csrc/group_gj.cuh
+REG_MODELS = ["hopper", "acrobot_impact", "cartpole_friction", "planar_push"]     # models whose latency configuration uses csrc/group_gj.cuh
 
 
 @pytest.mark.parametrize("name,reg", [(n, False) for n in CONFIGS] + [(n, True) for n in REG_MODELS])
