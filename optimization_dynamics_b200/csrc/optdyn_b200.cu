@@ -613,8 +613,19 @@ static int launch_rocket(od_handle* hd, RocketArgs& a) {
     a.h = hd->h; a.u_max = hd->params[0];
     a.opts.r_tol = hd->opts.r_tol; a.opts.kappa_eval_tol = hd->opts.kappa_eval_tol; a.opts.kappa_grad_tol = hd->opts.kappa_grad_tol;
     a.opts.ls_scale = hd->opts.ls_scale; a.opts.max_iter = hd->opts.max_iter; a.opts.max_ls = hd->opts.max_ls;
-    constexpr int BLOCK = 32;
-    rocket_kernel<BLOCK><<<(a.B + BLOCK - 1) / BLOCK, BLOCK, 0, hd->stream>>>(a);
+    // cooperative lanes (register Gauss–Jordan) while the batch cannot fill the machine with one thread per problem; OD_REG=0 or
+    // OD_LANES=1 force the thread-per-problem kernel
+    const int lanes = lanes_for(a.B);
+    if (reg_path() && lanes >= 8) {
+        constexpr int G = 8, PPB = 4;
+        rocket_kernel_g<G, PPB><<<(a.B + PPB - 1) / PPB, G * PPB, sizeof(double) * PPB * RocketG<G>::WS, hd->stream>>>(a);
+    } else if (reg_path() && lanes >= 4) {
+        constexpr int G = 4, PPB = 8;
+        rocket_kernel_g<G, PPB><<<(a.B + PPB - 1) / PPB, G * PPB, sizeof(double) * PPB * RocketG<G>::WS, hd->stream>>>(a);
+    } else {
+        constexpr int BLOCK = 32;
+        rocket_kernel<BLOCK><<<(a.B + BLOCK - 1) / BLOCK, BLOCK, 0, hd->stream>>>(a);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("rocket_kernel launch", e);
     hd->launches++;

@@ -77,12 +77,13 @@ extern "C" int hc_riccati(int NT, int T, int nq, int nu, const double* jac, cons
 }
 
 extern "C" int hc_rocket(int B, const double* x, const double* u, double h, double u_max, int proj, int want_grad, int proj_only,
-                         double* y, double* dx, double* du, double* uproj, double* duproj, int* status, int* iters) {
+                         double* y, double* dx, double* du, double* uproj, double* duproj, int* status, int* iters, int reg) {
     RocketArgs a; memset(&a, 0, sizeof(a));
     a.B = B; a.x = x; a.u = u; a.y = y; a.dx = dx; a.du = du; a.uproj = uproj; a.duproj = duproj; a.status = status; a.iters = iters;
     a.h = h; a.u_max = u_max; a.proj = proj; a.want_grad = want_grad; a.proj_only = proj_only;
     a.opts.r_tol = 1e-8; a.opts.kappa_eval_tol = 1e-4; a.opts.kappa_grad_tol = 1e-4; a.opts.ls_scale = 0.5; a.opts.max_iter = 100; a.opts.max_ls = 25;
-    for (int i = 0; i < B; ++i) rocket_one(a, i);
+    if (reg) { alignas(16) double ws[RocketG<1>::WS]; for (int i = 0; i < B; ++i) RocketG<1>::run(a, i, ws, 0); }
+    else for (int i = 0; i < B; ++i) rocket_one(a, i);
     return 0;
 }
 

@@ -90,13 +90,13 @@ def riccati(jac, lx, lu, lxx, luu, lux, nq, nu, reg=0.0):
     return K, k, dV, st
 
 
-def rocket(x, u, h, u_max, proj, want_grad=True, proj_only=False):
+def rocket(x, u, h, u_max, proj, want_grad=True, proj_only=False, reg=False):
     x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 12); B = x.shape[0]
     u = np.ascontiguousarray(u, dtype=np.float64).reshape(B, 3)
     y = np.zeros((B, 12)); dx = np.zeros((B, 12, 12)); du = np.zeros((B, 3, 12)); up = np.zeros((B, 3)); dup = np.zeros((B, 3, 3))
     st = np.zeros(B, dtype=np.int32); it = np.zeros(B, dtype=np.int32)
     rc = lib().hc_rocket(B, _p(x), _p(u), C.c_double(h), C.c_double(u_max), int(proj), int(want_grad), int(proj_only), _p(y), _p(dx), _p(du), _p(up), _p(dup),
-                         _p(st, C.c_int), _p(it, C.c_int))
+                         _p(st, C.c_int), _p(it, C.c_int), int(reg))
     assert rc == 0
     return dict(y=y, dx=dx, du=du, uproj=up, duproj=dup, status=st, iters=it)
 

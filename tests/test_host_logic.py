@@ -58,11 +58,12 @@ def test_residual_blocks_and_newton_direction_match_dense_oracle():
         assert np.abs(d - np.linalg.solve(rz, r)).max() < 1e-11
 
 
-@pytest.mark.parametrize("proj", [False, True])
-def test_rocket_templates_match_oracle(proj):
+@pytest.mark.parametrize("proj,reg", [(False, False), (True, False), (False, True), (True, True)])
+def test_rocket_templates_match_oracle(proj, reg):
+    """reg=True: the cooperative-lane solver (dense_ipg.cuh, register Gauss–Jordan) run with one lane."""
     x, u = W.rocket_batch(512, seed=1)
     o = O.rocket_batch(x, u, 0.05, 12.5, proj, True)
-    r = H.rocket(x, u, 0.05, 12.5, proj)
+    r = H.rocket(x, u, 0.05, 12.5, proj, reg=reg)
     ok = (o["status"] == 0) & (r["status"] == 0) & (o["margin"] > 1e-6)
     assert ok.mean() > 0.9
     assert np.abs(o["y"] - r["y"])[ok].max() < 1e-8
