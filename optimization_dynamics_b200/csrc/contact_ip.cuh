@@ -800,6 +800,8 @@ struct StepArgs {
     double* peer_out[8];
     // Packed output (q3/dq1/dq2/du point into one row of width NOUT, 16-byte aligned): the register path stores it as 16-byte pairs.
     int packed_out;
+    // Packed input (q2 = q1 + NQ, u = q1 + 2NQ, one stride): the register path loads the row cooperatively.
+    int in_packed;
     // Cross-GPU barrier fused into the kernel (replaces the separate barrier launch after the fused all-gather): every thread
     // fences its peer stores, the last block of the grid to finish publishes `sync_epoch` into slot `self_rank` of every peer's
     // flag array and waits until every peer has published it here.  sync_flags[r] = rank r's flag array (world × u64) as mapped
@@ -842,10 +844,32 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
         const double* p2 = a.q2 + (size_t)src * a.in_stride_q;
         const double* pu = a.u + (size_t)src * a.in_stride_u;
         const double* pe = (pert > 0) ? a.eta + (size_t)(pert - 1) * (2 * NQ + NU) : nullptr;
+        // One packed input row [q1 | q2 | u] per problem: the G lanes load it once between them (consecutive lanes, consecutive
+        // doubles — whole sectors even when the row lives in pinned host memory) and exchange the values by shuffle; otherwise
+        // every lane loads every value (same addresses within a group: a broadcast).
+        constexpr int NIN = 2 * NQ + NU;
+        double xin[NIN];
+        bool coop = false;
+        if constexpr (REG && G > 1) {
+            coop = a.in_packed != 0;
+            if (coop) {
+                double v[(NIN + G - 1) / G];
+#pragma unroll
+                for (int t = 0; t < (NIN + G - 1) / G; ++t) { const int e = g + G * t; v[t] = (e < NIN) ? p1[e] : 0.0; }
+#pragma unroll
+                for (int e = 0; e < NIN; ++e) xin[e] = Grp<G>::bcast(v[e / G], e % G, gmask);
+            }
+        }
+        if (!coop) {
+#pragma unroll
+            for (int k = 0; k < NQ; ++k) { xin[k] = p1[k]; xin[NQ + k] = p2[k]; }
+#pragma unroll
+            for (int k = 0; k < NU; ++k) xin[2 * NQ + k] = pu[k];
+        }
         double q2v[NQ];
 #pragma unroll
         for (int k = 0; k < NQ; ++k) {
-            double x1 = p1[k], x2 = p2[k];
+            double x1 = xin[k], x2 = xin[NQ + k];
             if (pe) { x1 += pe[k]; x2 += pe[NQ + k]; }
             const double v1 = (x2 - x1) / a.h;                 // src/dynamics.jl:84-86
             th[k] = x2 - a.h * v1;                             // RoboDojo.step!: q1 = q2 − h v1
@@ -853,7 +877,7 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
             q2v[k] = x2;
         }
 #pragma unroll
-        for (int k = 0; k < NU; ++k) th[2 * NQ + k] = pe ? pu[k] + pe[2 * NQ + k] : pu[k];
+        for (int k = 0; k < NU; ++k) th[2 * NQ + k] = pe ? xin[2 * NQ + k] + pe[2 * NQ + k] : xin[2 * NQ + k];
 #pragma unroll
         for (int k = 0; k < M::NF; ++k) th[2 * NQ + NU + k] = a.fric[k];
         th[M::NTH - 1] = a.h;
@@ -1082,7 +1106,7 @@ OD_HD void contact_rollout_one(const RolloutArgs& ra, const int r, double* ws, c
     for (int k = 0; k < 4; ++k) a.fric[k] = ra.fric[k];
     a.want_eval = 1; a.want_grad = 0; a.eta = nullptr; a.n_eta = 0;
     a.n_peers = 0; a.self_rank = 0; a.gather_row0 = 0; a.gather_width = 0;
-    a.packed_out = 0; a.sync_counter = nullptr; a.sync_epoch = 0;
+    a.packed_out = 0; a.in_packed = 0; a.sync_counter = nullptr; a.sync_epoch = 0;
     a.opts = ra.opts;
     const double alpha = ra.alpha ? ra.alpha[r] : 1.0;
     const double* ub = ra.ubar + (size_t)r * ra.ubar_stride;

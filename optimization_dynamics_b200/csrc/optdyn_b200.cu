@@ -287,7 +287,7 @@ int od_step_grad_packed_device(od_handle* hd, int B, const double* in, double* o
     OD_CUDA(cudaSetDevice(hd->device));
     const int inw = 2 * d.nq + d.nu, outw = d.nq + d.nq * inw;
     StepArgs a; memset(&a, 0, sizeof(a));
-    a.B = B; a.q1 = in; a.q2 = in + d.nq; a.u = in + 2 * d.nq; a.in_stride_q = inw; a.in_stride_u = inw;
+    a.B = B; a.q1 = in; a.q2 = in + d.nq; a.u = in + 2 * d.nq; a.in_stride_q = inw; a.in_stride_u = inw; a.in_packed = 1;
     a.q3 = out; a.dq1 = want_grad ? out + d.nq : nullptr; a.dq2 = out + d.nq + d.nq * d.nq; a.du = out + d.nq + 2 * d.nq * d.nq;
     a.out_stride_q3 = outw; a.out_stride_dq = outw; a.out_stride_du = outw;
     a.status = status; a.iters = iters; a.want_eval = want_eval; a.want_grad = want_grad;
@@ -304,7 +304,7 @@ int od_step_grad_packed_gather_device(od_handle* hd, int B, const double* in, lo
     const int inw = 2 * d.nq + d.nu, outw = d.nq + d.nq * inw;
     double* out = (double*)gather_buffers[rank] + (size_t)row0 * outw;
     StepArgs a; memset(&a, 0, sizeof(a));
-    a.B = B; a.q1 = in; a.q2 = in + d.nq; a.u = in + 2 * d.nq; a.in_stride_q = inw; a.in_stride_u = inw;
+    a.B = B; a.q1 = in; a.q2 = in + d.nq; a.u = in + 2 * d.nq; a.in_stride_q = inw; a.in_stride_u = inw; a.in_packed = 1;
     a.q3 = out; a.dq1 = out + d.nq; a.dq2 = out + d.nq + d.nq * d.nq; a.du = out + d.nq + 2 * d.nq * d.nq;
     a.out_stride_q3 = outw; a.out_stride_dq = outw; a.out_stride_du = outw;
     a.status = status; a.iters = iters; a.want_eval = 1; a.want_grad = 1;
@@ -328,7 +328,7 @@ int od_step_grad_packed_gather_sync_device(od_handle* hd, int B, const double* i
     const int inw = 2 * d.nq + d.nu, outw = d.nq + d.nq * inw;
     double* out = (double*)gather_buffers[rank] + (size_t)row0 * outw;
     StepArgs a; memset(&a, 0, sizeof(a));
-    a.B = B; a.q1 = in; a.q2 = in + d.nq; a.u = in + 2 * d.nq; a.in_stride_q = inw; a.in_stride_u = inw;
+    a.B = B; a.q1 = in; a.q2 = in + d.nq; a.u = in + 2 * d.nq; a.in_stride_q = inw; a.in_stride_u = inw; a.in_packed = 1;
     a.q3 = out; a.dq1 = out + d.nq; a.dq2 = out + d.nq + d.nq * d.nq; a.du = out + d.nq + 2 * d.nq * d.nq;
     a.out_stride_q3 = outw; a.out_stride_dq = outw; a.out_stride_du = outw;
     a.status = status; a.iters = iters; a.want_eval = 1; a.want_grad = 1;
