@@ -212,6 +212,8 @@ def test_rollouts_match_oracle_hopper_forward_pass(od, O):
     print("hopper forward pass: one-step max|q3-oracle|=%.2e  trajectory max|X-oracle|=%.2e" % (e1, np.abs(X - Xo).max()))
     assert np.abs(X - Xo).max() < 1e-6 and np.abs(U - Uo).max() < 1e-6
     assert np.abs(X[-1] - xbar).max() < 1e-4                              # α = 1e-5 ≈ the nominal trajectory
+    X3, U3 = od.rollout_batch(dyn, x1, ubar, xbar=xbar, K=K, k=k, alpha=alpha[:3])       # ragged: not a multiple of the block
+    assert np.array_equal(X3, X[:3]) and np.array_equal(U3, U[:3])
 
 
 @pytest.mark.parametrize("name", ["planar_push", "cartpole_friction", "acrobot_impact"])
@@ -254,6 +256,8 @@ def test_riccati_backward_pass_and_full_ilqr_iteration(od, O):
         assert np.abs(K[a] - Ko).max() <= 1e-9 * max(1.0, np.abs(Ko).max()) and np.abs(k[a] - ko).max() <= 1e-9 * max(1.0, np.abs(ko).max())
         assert np.abs(dV[a] - dVo).max() <= 1e-9 * max(1.0, np.abs(dVo).max())
     assert (dV[:, 0] < 0).all()                                                                 # descent direction
+    K3, k3, dV3, s3 = od.backward_pass_batch(dyn, jac[:3], lx[:3], lu[:3], lxx[:3], luu[:3], lux[:3])    # odd trajectory count
+    assert np.array_equal(K3, K[:3]) and np.array_equal(k3, k[:3]) and np.array_equal(dV3, dV[:3])
     # forward pass of trajectory 0 with its gains: 8 step sizes in one launch; α = 1e-5 stays on the nominal trajectory
     al = np.array([1.0, 0.5, 0.25, 0.125, 0.0625, 0.03125, 1e-3, 1e-5])
     Xn, Un, sn = od.rollout_batch(dyn, X[0, 0], U[0], xbar=X[0], K=K[0], k=k[0], alpha=al, return_status=True)
