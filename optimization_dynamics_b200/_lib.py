@@ -46,10 +46,11 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(SO_PATH):
+    path = os.environ.get("OD_B200_LIB", SO_PATH)      # A/B timing of differently built libraries (tools/micro/ab_time.sh)
+    if not os.path.exists(path):
         raise RuntimeError("liboptdyn_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
                            "optimization_dynamics_b200 has no CPU fallback")
-    L = C.CDLL(SO_PATH)
+    L = C.CDLL(path)
     vp, i, d = C.c_void_p, C.c_int, C.c_double
     dp, ip = c_double_p, c_int32_p
     sig = {

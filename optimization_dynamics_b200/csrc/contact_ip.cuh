@@ -23,6 +23,11 @@
 #include <math.h>
 #include "group_gj.cuh"
 
+// 1: the pivot row of every elimination step travels through the shared-memory staging area (GroupGJ::factor_sm), 0: by shuffles.
+#ifndef OD_GJ_SMEM
+#define OD_GJ_SMEM 1
+#endif
+
 // Every solver routine is __host__ __device__ so that tests/host_check.cu can single-step the very same template code on the
 // CPU against the oracle (a debugging aid for a GPU-less build container; liboptdyn_b200.so exports no host compute path).
 #ifndef OD_HD
@@ -158,28 +163,28 @@ struct ContactIP {
     OD_HD static void residual(const Z& z, const double* th, const double* trc, const double* trv, R& r, double& r_vio, double& k_vio) {
         double phi[NC1], psit[NP1], vT[NB1];
         M::eq(z.q, z.gam, z.b, th, trc, trv, r.d, phi, psit, vT);
-        double rv = 0.0, kv = 0.0;
+        MaxAcc rv, kv;                                         // ∞-norms of the equality rows / the bilinear rows
 #pragma unroll
-        for (int i = 0; i < NQ; ++i) rv = fmax(rv, fabs(r.d[i]));
+        for (int i = 0; i < NQ; ++i) rv.add(od_abs(r.d[i]));
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
-            r.rs[i] = z.s[i] - phi[i]; rv = fmax(rv, fabs(r.rs[i]));
-            r.rgam[i] = z.gam[i] * z.s[i]; kv = fmax(kv, fabs(r.rgam[i]));
+            r.rs[i] = z.s[i] - phi[i]; rv.add(od_abs(r.rs[i]));
+            r.rgam[i] = z.gam[i] * z.s[i]; kv.add(od_abs(r.rgam[i]));
         }
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
-            r.rpsi[k] = z.psi[k] - psit[k]; rv = fmax(rv, fabs(r.rpsi[k]));
+            r.rpsi[k] = z.psi[k] - psit[k]; rv.add(od_abs(r.rpsi[k]));
             double acc = z.psi[k] * z.spsi[k];
 #pragma unroll
             for (int j = M::cone_off(k); j < M::cone_off(k) + M::cone_dim(k); ++j) {
                 acc += z.b[j] * z.sb[j];
-                r.rc1[j] = z.psi[k] * z.sb[j] + z.spsi[k] * z.b[j]; kv = fmax(kv, fabs(r.rc1[j]));
+                r.rc1[j] = z.psi[k] * z.sb[j] + z.spsi[k] * z.b[j]; kv.add(od_abs(r.rc1[j]));
             }
-            r.rc0[k] = acc; kv = fmax(kv, fabs(acc));
+            r.rc0[k] = acc; kv.add(od_abs(acc));
         }
 #pragma unroll
-        for (int j = 0; j < NB; ++j) { r.rv[j] = vT[j] - z.sb[j]; rv = fmax(rv, fabs(r.rv[j])); }
-        r_vio = rv; k_vio = kv;
+        for (int j = 0; j < NB; ++j) { r.rv[j] = vT[j] - z.sb[j]; rv.add(od_abs(r.rv[j])); }
+        r_vio = rv.v; k_vio = kv.v;
     }
 
     // ---- linearise at z: model blocks → reduced matrix K → LU with partial pivoting (in the workspace) -----------------
@@ -198,7 +203,11 @@ struct ContactIP {
             for (int i = 0; i < NR; ++i) L.S(i, NR) = x[i];
             L.sync();
             fetch_rows<NR + 1>(L, L.a);
+#if OD_GJ_SMEM
+            L.ok = GJ::template factor_sm<PW>(L.a, L.piv, L.g, L.gmask, &L.S(0, 0));
+#else
             L.ok = GJ::factor(L.a, L.piv, L.g, L.gmask);
+#endif
         } else {
             assemble(z, th, trc, trv, L); factor(L);
         }
@@ -505,26 +514,26 @@ struct ContactIP {
         }
     }
     OD_HD static double step_length(const Z& z, const ConeRcp& c, const Z& D, double tau) {
-        double rho = 0.0, rho2 = 0.0;                          // two independent running maxima (shorter dependent chain)
+        MaxAcc rho, rho2;                                      // two independent running maxima (shorter dependent chain)
 #pragma unroll
-        for (int i = 0; i < NC; ++i) { rho = fmax(rho, D.gam[i] * c.gam[i]); rho2 = fmax(rho2, D.s[i] * c.s[i]); }
+        for (int i = 0; i < NC; ++i) { rho.add(D.gam[i] * c.gam[i]); rho2.add(D.s[i] * c.s[i]); }
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
             const int o = M::cone_off(k);
             if (M::cone_dim(k) == 1) {
-                rho = fmax(rho, (D.psi[k] - D.b[o]) * c.pm[k]); rho2 = fmax(rho2, (D.psi[k] + D.b[o]) * c.pp[k]);
-                rho = fmax(rho, (D.spsi[k] - D.sb[o]) * c.dm[k]); rho2 = fmax(rho2, (D.spsi[k] + D.sb[o]) * c.dp[k]);
+                rho.add((D.psi[k] - D.b[o]) * c.pm[k]); rho2.add((D.psi[k] + D.b[o]) * c.pp[k]);
+                rho.add((D.spsi[k] - D.sb[o]) * c.dm[k]); rho2.add((D.spsi[k] + D.sb[o]) * c.dp[k]);
             } else {
                 double bn = 1.0, bd = 0.0;                     // soc_step leaves (τ, den) when den > 0
                 soc_step<2>(z.psi[k], &z.b[o], D.psi[k], &D.b[o], 1.0, bn, bd);
-                rho = fmax(rho, bd);
+                rho.add(bd);
                 bn = 1.0; bd = 0.0;
                 soc_step<2>(z.spsi[k], &z.sb[o], D.spsi[k], &D.sb[o], 1.0, bn, bd);
-                rho2 = fmax(rho2, bd);
+                rho2.add(bd);
             }
         }
-        rho = fmax(rho, rho2);
-        return (rho > tau) ? tau / rho : 1.0;
+        rho.add(rho2.v);                                       // only a ratio above τ > 0 shortens the step: no clamp at 0 needed
+        return (rho.v > tau) ? tau * pivot_rcp(rho.v) : 1.0;        // rho > τ ≥ 0.95: the short reciprocal is safe (fastmath.cuh)
     }
 
     // Σ ⟨primal − aΔp, dual − aΔd⟩ over all cones
@@ -560,7 +569,7 @@ struct ContactIP {
             const double a_aff = step_length(z, rcp, D, 1.0);
             const double mu = cone_dot(z, D, 0.0) * (1.0 / (NCONE > 0 ? NCONE : 1));
             const double mu_aff = cone_dot(z, D, a_aff) * (1.0 / (NCONE > 0 ? NCONE : 1));
-            const double ratio = fmin(fmax(mu_aff / mu, 0.0), 1.0);
+            const double ratio = od_min(od_max(0.0, mu_aff * pivot_rcp(mu)), 1.0);   // μ > 0 at any non-converged iterate
             const double kappa = ratio * ratio * ratio * mu;      // max(σμ, κ_tol/undercut) with undercut = Inf
             // corrector right-hand side: r(z;κ) + Δaff_primal ∘ Δaff_dual on the bilinear rows
             R rc = r;
@@ -578,8 +587,8 @@ struct ContactIP {
                 rc.rc0[k] = (r.rc0[k] - kappa) + acc;
             }
             solve(L, z, rc, D);
-            const double viol = fmax(r_vio, k_vio);
-            alpha = step_length(z, rcp, D, fmax(0.95, 1.0 - viol * viol));
+            const double viol = od_max(r_vio, k_vio);
+            alpha = step_length(z, rcp, D, od_max(0.95, 1.0 - viol * viol));
         } else {
             solve_carried(L, z, r, D);                           // no cones: plain Newton direction, full step
             alpha = 1.0;
@@ -658,7 +667,11 @@ struct ContactIP {
         double a[RPL][NR + NTP];
         int piv[NR];
         fetch_rows<NR + NTP>(L, a);
+#if OD_GJ_SMEM
+        const bool ok = GJS::template factor_sm<PW>(a, piv, L.g, L.gmask, &L.S(0, 0));
+#else
         const bool ok = GJS::factor(a, piv, L.g, L.gmask);
+#endif
         L.sync();                                             // every lane has its rows: the staging area becomes the output row
 #pragma unroll
         for (int i = 0; i < NQ; ++i) {

@@ -22,6 +22,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <string.h>
+#include "fastmath.cuh"
 
 #ifndef OD_HD
 #define OD_HD __host__ __device__ __forceinline__
@@ -53,20 +54,6 @@ OD_HD unsigned abs_hi32(double v) {
     return (unsigned)__double2hiint(v) & 0x7fffffffu;
 #else
     unsigned long long b; memcpy(&b, &v, 8); return (unsigned)(b >> 32) & 0x7fffffffu;
-#endif
-}
-
-// Reciprocal of a pivot: hardware seed (MUFU.RCP64H, ≥ 20 bits) + two Newton steps = full double precision to within an ulp, in
-// 5 dependent instructions instead of the ~20 of the IEEE-rounded division sequence (it sits on the critical path of every step).
-OD_HD double pivot_rcp(double x) {
-#ifdef __CUDA_ARCH__
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    r = fma(r, fma(-x, r, 1.0), r);
-    r = fma(r, fma(-x, r, 1.0), r);
-    return r;
-#else
-    return 1.0 / x;
 #endif
 }
 
@@ -129,6 +116,74 @@ struct GroupGJ {
             double prow[NCOL];
 #pragma unroll
             for (int j = k + 1; j < NCOL; ++j) prow[j] = Grp<G>::bcast(pick(a, j, ws), wl, gm);
+#pragma unroll
+            for (int s = 0; s < RPL; ++s) {
+                const bool isp = own && (s == ws);
+                const double m = a[s][k] * inv;
+                a[s][k] = isp ? inv : m;
+                const double me = isp ? 0.0 : m;
+#pragma unroll
+                for (int j = k + 1; j < NCOL; ++j) a[s][j] -= me * prow[j];
+            }
+        }
+        return ok;
+    }
+
+    // factor() with the pivot row passed through shared memory instead of shuffles.  `S` is the staging area the rows were fetched
+    // from (row r at S + r·PITCH, PITCH even, 16-byte aligned, at least NCOL + NCOL%2 columns): on entry it still holds the matrix,
+    // so step 0 reads its pivot row straight from it; before every later step each lane re-publishes the columns ≥ k+1 of its own
+    // rows (16-byte stores, issued while the pivot search of the step is in flight) and the pivot row comes back as 16-byte
+    // broadcast loads.  Per matrix element that is 1.5 instructions (2 STS.128 + 1 LDS.128 per pair of columns) instead of the
+    // 4 of the register path (a 2-way select + 2 SHFL per double), and one scoreboard wait per pair instead of per word:
+    // 12×13 system: 129 memory instructions instead of 312 shuffles + selects.
+    // Hazards: a lane only ever writes its own rows; a lane running ahead re-publishes a former pivot row with unchanged values
+    // (its multiplier is forced to zero), so one warp barrier per step — between publishing and reading — is enough.
+    // Same arithmetic, in the same order, as factor().
+    template <int PITCH>
+    OD_HD static bool factor_sm(double (&a)[RPL][NCOL], int (&piv)[NR], const int g, const unsigned gm, double* S) {
+        static_assert(PITCH % 2 == 0 && PITCH >= NCOL + (NCOL % 2), "pairs of columns are moved as 16-byte words");
+        bool ok = true;
+        unsigned done = 0;
+#pragma unroll
+        for (int s = 0; s < RPL; ++s) if (s * G + g >= NR) done |= 1u << s;
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+            const int j0 = (k + 1) & ~1;                       // first column of the first 16-byte pair that holds a column > k
+            if (k > 0) {
+#pragma unroll
+                for (int s = 0; s < RPL; ++s) {
+                    const int r = s * G + g;
+                    if (G == 1 || (s + 1) * G <= NR || r < NR) {
+                        double2* dst = reinterpret_cast<double2*>(S + r * PITCH + j0);
+#pragma unroll
+                        for (int j = j0; j < NCOL; j += 2) dst[(j - j0) / 2] = make_double2(a[s][j], (j + 1 < NCOL) ? a[s][j + 1] : 0.0);
+                    }
+                }
+            }
+            unsigned key = 0;
+#pragma unroll
+            for (int s = 0; s < RPL; ++s) {
+                const unsigned ks = (abs_hi32(a[s][k]) & ~31u) | (unsigned)(s * G + g);
+                const unsigned kk = ((done >> s) & 1u) ? 0u : ks;
+                key = kk > key ? kk : key;
+            }
+            const double myinv = pivot_rcp(pick(a, k, (int)(key & 31u) >> LG));
+            key = Grp<G>::umax_all(key, gm);
+            ok = ok && (key >= 32u) && (key < 0x7ff00000u);
+            const int pr = (int)(key & 31u), wl = pr & (G - 1), ws = pr >> LG;
+            piv[k] = pr;
+            const double inv = Grp<G>::bcast(myinv, wl, gm);
+            const bool own = (g == wl);
+            if (own) done |= 1u << ws;
+#ifdef __CUDA_ARCH__
+            if (G > 1 && k > 0) __syncwarp(gm);               // (the reduction above is not a memory barrier)
+#endif
+            double prow[NCOL + 1];
+            {
+                const double2* src = reinterpret_cast<const double2*>(S + pr * PITCH + j0);
+#pragma unroll
+                for (int j = j0; j < NCOL; j += 2) { const double2 v = src[(j - j0) / 2]; prow[j] = v.x; prow[j + 1] = v.y; }
+            }
 #pragma unroll
             for (int s = 0; s < RPL; ++s) {
                 const bool isp = own && (s == ws);

@@ -192,3 +192,9 @@ extern "C" int hc_contact_K(int model, const double* z, const double* th, double
     }
     return 0;
 }
+
+// fastmath.cuh on the host: the same sin/cos code the kernels run (the reciprocal and the bit tricks have host twins there).
+extern "C" int hc_sincos(int n, const double* x, double* s, double* c) {
+    for (int i = 0; i < n; ++i) od_sincos(x[i], s + i, c + i);
+    return 0;
+}

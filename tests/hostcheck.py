@@ -107,3 +107,10 @@ def residual_and_direction(model, z, th):
     out = np.zeros(len(z)); d = np.zeros(len(z))
     assert lib().hc_contact_residual(MODELS[model], _p(z), _p(th), _p(out), _p(d)) == 0
     return out, d
+
+
+def sincos(x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    s = np.empty_like(x); c = np.empty_like(x)
+    assert lib().hc_sincos(x.size, _p(x), _p(s), _p(c)) == 0
+    return s, c

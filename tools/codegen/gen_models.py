@@ -94,7 +94,7 @@ def emit_function(fname, inputs, outputs, doc=""):
             if arg not in emitted:
                 emitted.add(arg)
                 d = paired[arg]
-                lines.append("    double %s, %s; sincos(%s, &%s, &%s);" % (d[sp.sin].name, d[sp.cos].name, PR.doprint(arg), d[sp.sin].name, d[sp.cos].name))
+                lines.append("    double %s, %s; od_sincos(%s, &%s, &%s);" % (d[sp.sin].name, d[sp.cos].name, PR.doprint(arg), d[sp.sin].name, d[sp.cos].name))
             continue
         lines.append("    const double %s = %s;" % (s_.name, PR.doprint(e)))
     for (oname, i), e in zip(slots, red):
@@ -316,7 +316,7 @@ def emit_trig(fname, inputs, args, arr):
             if sy in used:
                 lines.append("    const double %s = %s[%d];" % (sy.name, aname, i))
     for k, a in enumerate(args):
-        lines.append("    sincos(%s, &%s[%d], &%s[%d]);" % (PR.doprint(a), arr, 2 * k, arr, 2 * k + 1))
+        lines.append("    od_sincos(%s, &%s[%d], &%s[%d]);" % (PR.doprint(a), arr, 2 * k, arr, 2 * k + 1))
     if not args:
         lines.append("    (void)%s;" % arr)
     lines.append("}")
