@@ -62,17 +62,17 @@ OD_HD void soc_step(double l0, const double* l1, double d0, const double* d1, do
 #pragma unroll
     for (int i = 0; i < DIM; ++i) { ll -= l1[i] * l1[i]; lD -= l1[i] * (-d1[i]); }
     ll = fmax(ll, 1e-25);
-    const double inv_ll = 1.0 / ll;
-    const double inv_sq = sqrt(ll) * inv_ll;
+    const double inv_sq = od_rsqrt(ll);                       // short reciprocal square root / reciprocal / square root (fastmath.cuh)
+    const double inv_ll = inv_sq * inv_sq;
     const double rho_s = lD * inv_ll;
-    const double coef = (lD * inv_sq + (-d0)) / (l0 * inv_sq + 1.0);
+    const double coef = (lD * inv_sq + (-d0)) * pivot_rcp(l0 * inv_sq + 1.0);
     double nv = 0.0;
     if (DIM == 1) {
         nv = fabs(((-d1[0]) - coef * l1[0] * inv_sq) * inv_sq);
     } else {
 #pragma unroll
         for (int i = 0; i < DIM; ++i) { const double rv = ((-d1[i]) - coef * l1[i] * inv_sq) * inv_sq; nv += rv * rv; }
-        nv = sqrt(nv);
+        nv = od_sqrt(nv);
     }
     const double den = nv - rho_s;
     if (den > 0.0) frac_min(bn, bd, tau, den);

@@ -16,10 +16,12 @@ struct DenseIP {
 
     OD_HD static void residual(const double* z, const double* th, double* r, double& r_vio, double& k_vio) {
         M::res(z, th, r);
-        double rv = 0.0, kv = 0.0;
-        for (int i = 0; i < M::NEQ; ++i) rv = fmax(rv, fabs(r[i]));
-        for (int i = M::NEQ; i < NZ; ++i) kv = fmax(kv, fabs(r[i]));
-        r_vio = rv; k_vio = kv;
+        MaxAcc rv, kv;
+#pragma unroll
+        for (int i = 0; i < M::NEQ; ++i) rv.add(od_abs(r[i]));
+#pragma unroll
+        for (int i = M::NEQ; i < NZ; ++i) kv.add(od_abs(r[i]));
+        r_vio = rv.v; k_vio = kv.v;
     }
 
     OD_HD static bool lu_factor(double* A, int* piv) {
@@ -59,7 +61,7 @@ struct DenseIP {
             l1[0] = z[M::soc_d(c, 1)]; l1[1] = z[M::soc_d(c, 2)]; d1[0] = D[M::soc_d(c, 1)]; d1[1] = D[M::soc_d(c, 2)];
             soc_step<2>(z[M::soc_d(c, 0)], l1, D[M::soc_d(c, 0)], d1, tau, bn, bd);
         }
-        return bn / bd;
+        return bn * pivot_rcp(bd);                 // bd > 0 by construction (starts at 1, replaced only by positive denominators)
     }
     OD_HD static double cone_dot(const double* z, const double* D, double a) {
         double s = 0.0;

@@ -92,16 +92,16 @@ struct DenseIPG {
             double a[RPL][NZ + 1];
             int piv[NZ];
             fetch_rows<NZ + 1>(c, a);
-            const bool ok = GJ::factor(a, piv, c.g, c.gm);
+            const bool ok = GJ::template factor_sm<PW>(a, piv, c.g, c.gm, c.ws);     // pivot rows through the staging area (group_gj.cuh)
             if (active && !ok) { status = ST_FAIL; active = false; }
             double dl[NZ];
             if (NCONE > 0) {
                 double da[NZ];
                 GJ::extract(a, piv, 0, da, c.gm);
                 const double a_aff = S::step_length(z, da, 1.0);
-                const double mu = S::cone_dot(z, da, 0.0) / (NCONE > 0 ? NCONE : 1);
-                const double mu_aff = S::cone_dot(z, da, a_aff) / (NCONE > 0 ? NCONE : 1);
-                const double ratio = fmin(fmax(mu_aff / mu, 0.0), 1.0);
+                const double mu = S::cone_dot(z, da, 0.0) * (1.0 / (NCONE > 0 ? NCONE : 1));
+                const double mu_aff = S::cone_dot(z, da, a_aff) * (1.0 / (NCONE > 0 ? NCONE : 1));
+                const double ratio = od_min(od_max(0.0, mu_aff * pivot_rcp(mu)), 1.0);
                 const double kappa = ratio * ratio * ratio * mu;
 #pragma unroll
                 for (int i = 0; i < NZ; ++i) dl[i] = r[i];
@@ -120,8 +120,8 @@ struct DenseIPG {
                 double xm[RPL];
                 GJ::mine(dl, xm, c.g);
                 GJ::solve(a, piv, xm, dl, c.g, c.gm);
-                const double viol = fmax(r_vio, k_vio);
-                alpha = S::step_length(z, dl, fmax(0.95, 1.0 - viol * viol));
+                const double viol = od_max(r_vio, k_vio);
+                alpha = S::step_length(z, dl, od_max(0.95, 1.0 - viol * viol));
             } else {
                 GJ::extract(a, piv, 0, dl, c.gm);
                 alpha = 1.0;
@@ -153,7 +153,7 @@ struct DenseIPG {
         double a[RPL][NZ + NTHP];
         int piv[NZ];
         fetch_rows<NZ + NTHP>(c, a);
-        const bool ok = GJS::factor(a, piv, c.g, c.gm);
+        const bool ok = GJS::template factor_sm<PW>(a, piv, c.g, c.gm, c.ws);
 #pragma unroll
         for (int i = 0; i < NROW; ++i) {
             const int wl = piv[i] & (G - 1), ws = piv[i] >> Grp<G>::LG;

@@ -31,6 +31,39 @@ OD_HD double pivot_rcp(double x) {
 #endif
 }
 
+// 1/sqrt(x) and sqrt(x), x > 0: hardware seed (MUFU.RSQ64H) + two Newton steps (+ one correction for sqrt) ≈ 1 ulp, in 9 / 13
+// instructions instead of the ≈ 30 of the IEEE-rounded sqrt() followed by a division.  Used by the 3-D second-order-cone step
+// length (planar push, rocket thrust projection), eight times per iteration.  tools/micro/rcp_test.cu measures both on the device.
+OD_HD double od_rsqrt(double x) {
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = fma(0.5 * y, fma(-x * y, y, 1.0), y);
+    y = fma(0.5 * y, fma(-x * y, y, 1.0), y);
+    return y;
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+OD_HD double od_sqrt(double x) {
+#ifdef __CUDA_ARCH__
+    const double y = od_rsqrt(x);
+    double s = x * y;
+    s = fma(fma(-s, s, x), 0.5 * y, s);
+    return (x == 0.0) ? 0.0 : s;
+#else
+    return sqrt(x);
+#endif
+}
+
+// x^N for a compile-time N by square-and-multiply (the generated planar-push code needs x^8 … x^10: 4 multiplications instead of 9)
+template <int N> OD_HD double ipow(double x) {
+    static_assert(N >= 1, "positive integer power");
+    if (N == 1) return x;
+    const double h = ipow<(N > 1 ? N / 2 : 1)>(x);
+    return (N % 2) ? h * h * x : h * h;
+}
+
 // max / min as one compare + select (3 instructions).  fmax()/fmin() expand to ≈ 8 (DSETP.MAX, selects, NaN quieting, moves), and
 // the step-length rule and the residual norms take ≈ 45 of them per iteration.  A NaN in the SECOND argument is ignored (as fmax
 // does); the first argument is the running value and is never NaN where these are used.

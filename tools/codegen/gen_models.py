@@ -31,16 +31,27 @@ class Printer(C99CodePrinter):
             n = int(e)
             if n == -1:
                 return "(1.0/(%s))" % self._print(b)
-            if 0 < n <= 12:
+            if 0 < n <= 3:
                 s = self.parenthesize(b, 1000)
                 return "(" + "*".join([s] * n) + ")"
-            if -12 <= n < 0:
+            if -3 <= n < 0:
                 s = self.parenthesize(b, 1000)
                 return "(1.0/(" + "*".join([s] * (-n)) + "))"
+            if 3 < n <= 64:                                   # square-and-multiply (fastmath.cuh): x^10 in 4 multiplications, not 9
+                return "ipow<%d>(%s)" % (n, self._print(b))
+            if -64 <= n < -3:
+                return "(1.0/ipow<%d>(%s))" % (-n, self._print(b))
         if e == sp.Rational(1, 2):
             return "sqrt(%s)" % self._print(b)
         if e == -sp.Rational(1, 2):
             return "rsqrt_d(%s)" % self._print(b)
+        if e.is_Rational and e.q == 2 and abs(e.p) <= 9:          # b^(n/2), n odd: integer power times one (r)sqrt instead of pow()
+            n = (abs(int(e.p)) - 1) // 2
+            sb = self.parenthesize(b, 1000)
+            ip = "*".join([sb] * n)
+            if e.p > 0:
+                return "(%s*sqrt(%s))" % (ip, self._print(b))
+            return "(rsqrt_d(%s)/(%s))" % (self._print(b), ip)
         return "pow(%s, %s)" % (self._print(b), self._print(sp.Float(e) if e.is_Rational else e))
 
     def _print_Rational(self, expr):
@@ -305,11 +316,41 @@ def hoist_trig(expr_lists, qsyms):
     return new_lists, const, var, syms
 
 
-def emit_trig(fname, inputs, args, arr):
+def hoist_roots(expr_lists, den=10):
+    """Fractional powers b^(m/den) (the 10-norm signed distance of the planar push and its derivatives: exponents −9/10, −9/5,
+    −19/10, −14/5, 1/10 of ONE base) are rewritten as b^k · W^r with W = b^(1/den) a table symbol and |r| ≤ den/2, so that an
+    evaluation point costs one pow() (in trig_var) instead of one per distinct exponent (12 in the planar-push Jacobian code).
+    The base b itself is tabulated too.  Returns (new lists, bases, root symbols, base symbols); the caller maps the symbols
+    into the trv table."""
+    bases = []
+    for lst in expr_lists:
+        for e in lst:
+            for p in sp.sympify(e).atoms(sp.Pow):
+                if p.exp.is_Rational and not p.exp.is_Integer and den % p.exp.q == 0 and p.exp.q != 2 and p.base not in bases:
+                    bases.append(p.base)
+    if not bases:
+        return expr_lists, [], [], []
+    bases = sorted(bases, key=lambda a: sp.default_sort_key(a))
+    syms = [sp.Symbol("rt%d" % k, positive=True) for k in range(len(bases))]
+    bsyms = [sp.Symbol("rb%d" % k, positive=True) for k in range(len(bases))]      # the base itself is tabulated next to its root
+
+    def rewrite(p):
+        if not (p.is_Pow and p.exp.is_Rational and not p.exp.is_Integer and den % p.exp.q == 0 and p.exp.q != 2 and p.base in bases):
+            return p
+        m = int(p.exp * den)
+        k = int(sp.floor(sp.Rational(m, den) + sp.Rational(1, 2)))
+        r = m - den * k
+        return bsyms[bases.index(p.base)] ** k * syms[bases.index(p.base)] ** r
+
+    new_lists = [[sp.sympify(e).replace(lambda x: x.is_Pow, rewrite) for e in lst] for lst in expr_lists]
+    return new_lists, bases, syms, bsyms
+
+
+def emit_trig(fname, inputs, args, arr, roots=(), root_den=10):
     lines = ["__host__ __device__ __forceinline__ void %s(%s, double* __restrict__ %s) {" % (
         fname, ", ".join("const double* __restrict__ %s" % n for n, _ in inputs), arr)]
     used = set()
-    for a in args:
+    for a in list(args) + list(roots):
         used |= a.free_symbols
     for aname, syms in inputs:
         for i, sy in enumerate(syms):
@@ -317,7 +358,14 @@ def emit_trig(fname, inputs, args, arr):
                 lines.append("    const double %s = %s[%d];" % (sy.name, aname, i))
     for k, a in enumerate(args):
         lines.append("    od_sincos(%s, &%s[%d], &%s[%d]);" % (PR.doprint(a), arr, 2 * k, arr, 2 * k + 1))
-    if not args:
+    if roots:                                         # b^(1/den) of the hoisted bases; they may use the sin/cos entries above
+        for k in range(2 * len(args)):
+            lines.append("    const double %s%d = %s[%d];" % (arr, k, arr, k))
+        for k, bexpr in enumerate(roots):
+            o = 2 * len(args) + 2 * k
+            lines.append("    %s[%d] = %s;" % (arr, o + 1, PR.doprint(bexpr)))
+            lines.append("    %s[%d] = pow(%s[%d], %s);" % (arr, o, arr, o + 1, repr(1.0 / root_den)))
+    if not args and not roots:
         lines.append("    (void)%s;" % arr)
     lines.append("}")
     return "\n".join(lines) + "\n"
@@ -336,16 +384,25 @@ def gen_contact(m):
               J(d, q, NQ), J(d, gam, NC), J(d, b, NB), J(phi, q, NQ), J(vT, q, NQ), J(psit, gam, NC),
               J(d, thp, len(thp)), J(vT, thp, len(thp))]
     groups, targs_c, targs_v, tsyms = hoist_trig(groups, q)
-    NTC, NTV = 2 * len(targs_c), 2 * len(targs_v)
+    groups, rbases, rsyms, rbsyms = hoist_roots(groups)
+    assert all(bx.free_symbols & (set(q) | set(tsyms["v"])) for bx in rbases), "a θ-only root would belong in trig_const"
+    rmap = {}
+    for k in range(len(rbases)):                       # table layout after the sin/cos pairs: [root, base] per hoisted base
+        rmap[rsyms[k]] = sp.Symbol("trv%d" % (2 * len(targs_v) + 2 * k), real=True)
+        rmap[rbsyms[k]] = sp.Symbol("trv%d" % (2 * len(targs_v) + 2 * k + 1), real=True)
+        tsyms["v"] = tsyms["v"] + [rmap[rsyms[k]], rmap[rbsyms[k]]]
+    if rmap:
+        groups = [[e.xreplace(rmap) for e in lst] for lst in groups]
+    NTC, NTV = 2 * len(targs_c), 2 * len(targs_v) + 2 * len(rbases)
     ins = [("q", q), ("gam", gam), ("b", b), ("th", th), ("trc", tsyms["c"]), ("trv", tsyms["v"])]
 
     out = ["// GENERATED by tools/codegen/gen_models.py — do not edit.  Model: %s" % m["name"],
            "// Block-form residual pieces of the contact-implicit step (see csrc/contact_ip.cuh for the layout).",
-           "// sin/cos are hoisted: trig_const(θ) once per problem, trig_var(q,θ) once per candidate point; eq/jac/jacth take the tables.",
+           "// sin/cos (and tenth roots) are hoisted: trig_const(θ) once per problem, trig_var(q,θ) once per candidate point; eq/jac/jacth take the tables.",
            "#pragma once", "namespace od { namespace gen_%s {" % m["name"],
            "constexpr int NQ = %d, NU = %d, NC = %d, NP = %d, NB = %d, NTH = %d, NTC = %d, NTV = %d;" % (NQ, NU, NC, NP, NB, m["NTH"], NTC, NTV), ""]
     out.append(emit_trig("trig_const", [("th", th)], targs_c, "trc"))
-    out.append(emit_trig("trig_var", [("q", q), ("th", th)], targs_v, "trv"))
+    out.append(emit_trig("trig_var", [("q", q), ("th", th)], targs_v, "trv", roots=rbases))
     total = {}
     src, total["eq"] = emit_function("eq", ins, [("d", groups[0]), ("phi", groups[1]), ("psit", groups[2]), ("vT", groups[3])],
                                      "d(q,γ,b;θ), ϕ(q), ψ̂(γ;θ), vT(q;θ)")

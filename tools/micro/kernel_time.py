@@ -24,5 +24,6 @@ for _ in range(reps): st.step_grad_packed(xin, out, s, it)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
 itn = (it.cpu().numpy() & 0xFFFF)
-print("%s B=%d lanes=%s reg=%s: %.4f ms/launch  %.3e solves/s  converged %.4f  iters mean %.2f max %d" % (
-    name, B, os.environ.get("OD_LANES", "auto"), os.environ.get("OD_REG", "1"), ms, B / (ms * 1e-3), float((s == 0).float().mean()), itn.mean(), itn.max()))
+ck = float(out[s == 0].abs().sum())
+print("%s B=%d lanes=%s reg=%s: %.4f ms/launch  %.3e solves/s  converged %.4f  iters mean %.2f max %d  checksum %.12e" % (
+    name, B, os.environ.get("OD_LANES", "auto"), os.environ.get("OD_REG", "1"), ms, B / (ms * 1e-3), float((s == 0).float().mean()), itn.mean(), itn.max(), ck))
