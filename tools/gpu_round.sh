@@ -13,3 +13,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --cs
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:contact_step_kernel -s 3 -c 2 -o gpurun_out/${TAG}_prof -f \
     python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full_bench.log 2>&1
 tail -3 gpurun_out/${TAG}_smoke.log; tail -5 gpurun_out/${TAG}_pytest_gpu.log; cat gpurun_out/${TAG}_bench.json; tail -2 gpurun_out/${TAG}_bench.err
+# the same kernel with one warp per SM (592 problems): the stall picture of an isolated warp, for the latency analysis in DESIGN.md
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:contact_step_kernel -s 3 -c 1 -o gpurun_out/${TAG}_prof_iso -f \
+    python tools/micro/kernel_time.py hopper 592 5 > gpurun_out/${TAG}_ncu_iso.log 2>&1
+ls -la gpurun_out/ | tail -15
