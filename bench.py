@@ -7,8 +7,9 @@
 A "step" = one pass of the hot path over one batch: every rank solves its B (q1,q2,u) hopper problems (q3 at κ_eval = 1e-4 and
 ∂q3/∂(q1,q2,u1) at κ_grad = 1e-3 — what f + fx + fu deliver, reference src/dynamics.jl:81-128) with inputs resident in HBM and,
 for N > 1, all-gathers the packed 352-B output rows so that every rank holds all Jacobians for the sequential Riccati pass
-(weak scaling: B per GPU fixed).  Timed on the device with CUDA events around each step; L2 is flushed between steps (outside
-the event pair).  `e2e` is the same metric through the public host API (ImplicitDynamics.step_grad_packed → C ABI) with pinned
+(weak scaling: B per GPU fixed).  Timed on the device with CUDA events around each step; the inputs of a step are kept out
+of L2 by reading a different device copy of the batch every step from a pool larger than L2 (`--l2 pool`, default) or by a
+256 MiB memset before every step, outside the event pair (`--l2 flush`).  `e2e` is the same metric through the public host API (ImplicitDynamics.step_grad_packed → C ABI) with pinned
 HOST buffers, H2D + kernel + D2H inside the timed region.
 
 `--impl reference` times the CPU restatement of the reference path (oracle/, kind "port": Julia and RoboDojo.jl are not
@@ -169,6 +170,10 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extra", action="store_true", help="also report a saturating batch (262144 per GPU) in the JSON line")
+    ap.add_argument("--l2", default="pool", choices=["pool", "flush"],
+                    help="how inputs are kept out of L2 between timed steps: 'pool' = every step reads another copy of the batch from a "
+                         "pool of device buffers larger than L2 (each buffer is used once per pass over the pool); 'flush' = a 256 MiB "
+                         "memset before every step (it also evicts the kernel's code, which a solver loop would find cached)")
     ap.add_argument("--collective", default="fused", choices=["fused", "fused-kernel-barrier", "fused-launch-barrier", "nccl"],
                     help="N>1: 'fused' = all-gather fused into the kernel over NVLink peer memory, cross-rank barrier fused as well up to 4 ranks "
                          "(falls back to nccl if symmetric memory is unavailable); 'fused-kernel-barrier' / 'fused-launch-barrier' force the "
@@ -211,6 +216,19 @@ def main():
     status = torch.empty((B,), dtype=torch.int32, device=dev)
     gathered = torch.empty((B_total, stepper.out_width), dtype=torch.float64, device=dev) if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # 2× the 126 MB L2
+    # --l2 pool: P device copies of the batch, P·B·80 B ≥ 1.05 × L2 (B200: 126 MB), used round-robin — the rows a step reads were
+    # last touched a whole pool (> L2) of traffic ago, so they come from HBM, while the kernel's instructions stay cached as they
+    # would in a solver loop.  The pool is flushed once after it has been filled.
+    pool = None
+    if args.l2 == "pool":
+        l2_bytes = torch.cuda.get_device_properties(dev).L2_cache_size
+        P = max(2, int(1.05 * l2_bytes // (B * BYTES_IN)) + 1 + args.warmup)
+        pool = xin.unsqueeze(0).repeat(P, 1, 1).contiguous()
+        flush.zero_()
+        torch.cuda.synchronize()
+
+    def batch_in(k):               # inputs of timed step k (warm-up steps take the buffers from the end of the pool)
+        return xin if pool is None else pool[k % pool.shape[0]]
     fused = None
     if world > 1 and args.collective != "nccl":
         okf = torch.ones(1, device=dev)
@@ -223,7 +241,7 @@ def main():
         if okf.item() == 0:
             fused = None
 
-    def step():
+    def step(xin=xin):
         if fused is not None:
             fused.step(xin, status)
             return
@@ -236,8 +254,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        flush.zero_(); step()
+    for w in range(args.warmup):
+        if pool is None:
+            flush.zero_(); step()
+        else:
+            step(batch_in(-1 - w))
     barrier()
     clocks = ClockSampler(local)
     clocks.run()
@@ -248,14 +269,16 @@ def main():
     barrier()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
-        flush.zero_()
+        if pool is None:
+            flush.zero_()
+        xk = batch_in(k)
         starts[k].record()
         if fused is not None:
-            fused.launch(xin, status)
+            fused.launch(xk, status)
             kmid[k].record()
             fused.barrier()
         else:
-            stepper.step_grad_packed(xin, out, status)
+            stepper.step_grad_packed(xk, out, status)
             kmid[k].record()
             if world > 1:
                 all_gather_rows(out, B_total, gathered)
@@ -330,7 +353,10 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "hopper gait contact step + IFT gradient (RoboDojo hopper, nq=4, nz=20), batch %d per GPU, h=0.05, "
                                    "kappa_eval=1e-4, kappa_grad=1e-3, r_tol=1e-8 (BASELINE.json configs[3])" % B,
-                       "batch_per_gpu": B, "global_batch": B_total, "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
+                       "batch_per_gpu": B, "global_batch": B_total, "l2": ("flushed between timed steps (256 MiB memset outside the event pair)" if pool is None else
+                              "inputs larger than L2: every timed step reads another device copy of the batch from a pool of %d buffers "
+                              "(%.0f MB > %.0f MB L2; flushed once after filling), so its rows come from HBM; no per-step flush" % (
+                                  pool.shape[0], pool.numel() * 8 / 1e6, torch.cuda.get_device_properties(dev).L2_cache_size / 1e6)),
                        "collective": ("none (1 GPU)" if world == 1 else
                                       ("all-gather and cross-rank barrier fused into the kernel: P2P stores of each finished 352-B row into every rank's buffer over NVLink, "
                                        "completion flags published by the last block of each rank" if fused.sync == "kernel" else
