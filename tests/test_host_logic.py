@@ -3,6 +3,7 @@ template code the CUDA kernels instantiate, so the reduced-system algebra is che
 exports every symbol include/optdyn_b200.h declares and fails loudly without a CUDA device; (3) host-side helpers."""
 import ctypes as C
 import os
+import sys
 import re
 
 import numpy as np
@@ -220,3 +221,27 @@ def test_fast_math_accuracy():
     assert s[0] == 0.0 and c[0] == 1.0
     assert np.abs(s[:7] - np.sin(x[:7])).max() < 2.5e-16 and np.abs(c[:7] - np.cos(x[:7])).max() < 2.5e-16
     assert np.isnan(s[7]) and np.isnan(c[7]) and np.isnan(s[8]) and np.isnan(c[8])
+
+
+def test_generated_model_code_is_up_to_date(tmp_path):
+    """csrc/gen/*.cuh are committed generator output (tools/codegen/gen_models.py, the successor of the reference's
+    deps/build.jl): regenerating must reproduce them byte for byte — including the tabulated tenth roots of the planar push."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_models", os.path.join(root, "tools", "codegen", "gen_models.py"))
+    G = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(G)
+    G.OUT = str(tmp_path)
+    argv = sys.argv
+    try:
+        sys.argv = ["gen_models.py"]
+        G.main()
+    finally:
+        sys.argv = argv
+    gen_dir = os.path.join(root, "optimization_dynamics_b200", "csrc", "gen")
+    names = sorted(f for f in os.listdir(gen_dir) if f.endswith(".cuh"))
+    assert names == sorted(os.listdir(str(tmp_path)))
+    for f in names:
+        assert open(os.path.join(gen_dir, f)).read() == open(os.path.join(str(tmp_path), f)).read(), f
+    pp = open(os.path.join(gen_dir, "model_planar_push.cuh")).read()
+    assert pp.count("pow(") == 1 and "ipow<" in pp            # one tenth root per evaluation point, integer powers by squaring
