@@ -5,12 +5,14 @@
 // one warp per SM sub-partition and the kernel time is the dependent-instruction latency of the slowest problem.
 //
 // Layout: row r of the NR×NCOL augmented matrix [K | right-hand sides] lives in lane g = r mod G, slot s = r div G, entirely in
-// registers (a[s][j], every j a compile-time index).  Nothing touches shared memory:
+// registers (a[s][j], every j a compile-time index):
 //   * pivot search  = per-lane max over its slots + log2(G) shuffle rounds on a 32-bit key (high word of |a|, row index in the low
 //                     5 bits — partial pivoting to ~15 significant bits of the candidates, ties broken by row index);
 //   * row exchange  = none: pivoting is implicit (the pivot row of step k stays where it is, `piv[k]` remembers it);
-//   * elimination   = the pivot row is broadcast with shuffles, every lane updates its own rows (all rows, above and below: Gauss–
-//                     Jordan costs the same as LU when rows are spread over lanes, and it needs no back-substitution).
+//   * elimination   = the pivot row reaches every lane — through the shared-memory staging area the rows came from (factor_sm,
+//                     the shipped path: 16-byte stores and broadcast loads) or by shuffles (factor) — and every lane updates its
+//                     own rows (all rows, above and below: Gauss–Jordan costs the same as LU when rows are spread over lanes, and
+//                     it needs no back-substitution).
 // After factor(): column k (< NR) of row r holds the multiplier that step k applied to row r (1/pivot for the pivot row itself),
 // so further right-hand sides can be pushed through the same elimination (solve()); the carried columns hold the reduced
 // right-hand sides, x_k = a[piv[k]][NR + c] / pivot_k (extract()).

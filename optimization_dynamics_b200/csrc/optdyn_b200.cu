@@ -186,8 +186,8 @@ static int lanes_for(int B, bool heavy = false) {
     // planar push (20×20 reduced system, 35 variables): measured 1024 problems 5.2 / 4.1 / 3.4 ms with 4 / 8 / 16 lanes,
     // 25 600 problems 12.0 / 10.0 ms with 4 / 8 lanes (register path; shared-memory LU: 5.3 and 12.0 ms)
     if (heavy) return B <= 4096 ? 16 : 8;
-    if (B <= 8192) return 8;       // measured on B200 (hopper): 4096 problems 0.099 ms with 8 lanes, 0.106 with 4, 0.127 with 16, 0.176 with 1
-    return 4;                      // 262144 problems: 62 M solves/s with 4 lanes (register path) vs 57 M with 1 lane (shared-memory LU)
+    if (B <= 8192) return 8;       // measured on B200 (hopper): 4096 problems 0.0745 ms with 8 lanes, 0.0759 with 4 (earlier kernel: 0.127 with 16, 0.176 with 1)
+    return 4;                      // 262144 problems: 87 M solves/s with 4 lanes (register path); 1 lane (shared-memory LU) was 57 M against 62 M before
 }
 static bool reg_path() {
     static int v = -1;
