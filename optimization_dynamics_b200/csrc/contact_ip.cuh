@@ -444,7 +444,12 @@ struct ContactIP {
         if constexpr (REG) {
             double xm[RPL];
             GJ::mine(x, xm, L.g);
+#if OD_EXTRACT_SMEM && OD_GJ_SMEM
+            if constexpr (PW >= GJ::CINV + 2) GJ::template solve_sm<PW>(L.a, L.piv, xm, x, L.g, L.gmask, &L.S(0, 0));
+            else GJ::solve(L.a, L.piv, xm, x, L.g, L.gmask);
+#else
             GJ::solve(L.a, L.piv, xm, x, L.g, L.gmask);
+#endif
         } else {
             lu_solve(L, x, &L.X(L.g, 0));
         }
@@ -454,7 +459,12 @@ struct ContactIP {
     OD_HD static void solve_carried(const Lin& L, const Z& z, const R& r, Z& D) {
         if constexpr (REG) {
             double x[NR];
+#if OD_EXTRACT_SMEM && OD_GJ_SMEM
+            if constexpr (PW >= GJ::CINV + 2) GJ::template extract_sm<PW>(L.a, L.piv, 0, x, L.g, L.gmask, &L.S(0, 0));
+            else GJ::extract(L.a, L.piv, 0, x, L.gmask);
+#else
             GJ::extract(L.a, L.piv, 0, x, L.gmask);
+#endif
             expand(L, r, x, D);
         } else {
             solve(L, z, r, D);

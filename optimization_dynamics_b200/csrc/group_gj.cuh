@@ -30,6 +30,13 @@
 #define OD_HD __host__ __device__ __forceinline__
 #endif
 
+// 1 (prepared experiment, not measured yet): the inverse pivots are kept in the shared-memory mirror and extract() / the tail of
+// solve() publish each lane's scaled rows there and gather the solution with plain loads (extract_sm / solve_sm) instead of two
+// slot selects, a multiply and two shuffles per unknown.  Static count on the hopper kernel: see DESIGN.md §9.
+#ifndef OD_EXTRACT_SMEM
+#define OD_EXTRACT_SMEM 0
+#endif
+
 namespace od {
 
 template <int G> struct Grp {
@@ -63,6 +70,7 @@ template <int NR, int NCOL, int G>
 struct GroupGJ {
     static constexpr int RPL = (NR + G - 1) / G;      // rows (slots) per lane
     static constexpr int LG = Grp<G>::LG;
+    static constexpr int CINV = NCOL + (NCOL % 2), CSOL = CINV + 1;   // OD_EXTRACT_SMEM: spare mirror columns (inverse pivot, scaled solution)
     static_assert(RPL * G <= 32, "row index must fit the 5 low key bits");
     static_assert(NCOL >= NR, "augmented matrix");
 
@@ -181,6 +189,7 @@ struct GroupGJ {
 #ifdef __CUDA_ARCH__
             if (G > 1 && k > 0) __syncwarp(gm);               // (the reduction above is not a memory barrier)
 #endif
+            if (OD_EXTRACT_SMEM && PITCH >= CINV + 2) S[pr * PITCH + CINV] = inv;      // every lane stores the same value: no barrier needed to read it back
             double prow[NCOL + 1];
             {
                 const double2* src = reinterpret_cast<const double2*>(S + pr * PITCH + j0);
@@ -207,6 +216,48 @@ struct GroupGJ {
             const int wl = piv[k] & (G - 1), ws = piv[k] >> LG;
             sol[k] = Grp<G>::bcast(pick(a, NR + c, ws) * pick(a, k, ws), wl, gm);
         }
+    }
+
+    // OD_EXTRACT_SMEM variants.  Row r's inverse pivot sits in S[r·PITCH + CINV] (factor_sm); every lane scales its own rows,
+    // publishes them in column CSOL and reads unknown k from the row that was the pivot of step k.
+    template <int PITCH>
+    OD_HD static void gather_sm(const double (&y)[RPL], const int (&piv)[NR], double* sol, const int g, const unsigned gm, double* S) {
+#ifdef __CUDA_ARCH__
+        if (G > 1) __syncwarp(gm);                                // earlier readers of column CSOL are done
+#endif
+#pragma unroll
+        for (int s = 0; s < RPL; ++s) {
+            const int r = s * G + g;
+            if (G == 1 || (s + 1) * G <= NR || r < NR) S[r * PITCH + CSOL] = y[s] * S[r * PITCH + CINV];
+        }
+#ifdef __CUDA_ARCH__
+        if (G > 1) __syncwarp(gm);
+#endif
+#pragma unroll
+        for (int k = 0; k < NR; ++k) sol[k] = S[piv[k] * PITCH + CSOL];
+    }
+    template <int PITCH>
+    OD_HD static void extract_sm(const double (&a)[RPL][NCOL], const int (&piv)[NR], const int c, double* sol, const int g, const unsigned gm, double* S) {
+        double y[RPL];
+#pragma unroll
+        for (int s = 0; s < RPL; ++s) y[s] = a[s][NR + c];
+        gather_sm<PITCH>(y, piv, sol, g, gm, S);
+    }
+    template <int PITCH>
+    OD_HD static void solve_sm(const double (&a)[RPL][NCOL], const int (&piv)[NR], double (&x)[RPL], double* sol, const int g, const unsigned gm, double* S) {
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+            const int wl = piv[k] & (G - 1), ws = piv[k] >> LG;
+            const double xp = Grp<G>::bcast(pickv(x, ws), wl, gm);
+            const bool own = (g == wl);
+#pragma unroll
+            for (int s = 0; s < RPL; ++s) {
+                const bool isp = own && (s == ws);
+                const double me = isp ? 0.0 : a[s][k];
+                x[s] -= me * xp;
+            }
+        }
+        gather_sm<PITCH>(x, piv, sol, g, gm, S);
     }
 
     // A further right-hand side (x = this lane's rows of it) through the stored elimination; solution replicated in every lane.
