@@ -53,6 +53,14 @@ struct DenseIPG {
         }
     }
 
+    // solution of the carried (affine) right-hand side, replicated in every lane
+    OD_HD static void affine(const double (&a)[RPL][NZ + 1], const int (&piv)[NZ], double* sol, const Ctx& c) {
+#if OD_EXTRACT_SMEM
+        if constexpr (PW >= GJ::CINV + 2) { GJ::template extract_sm<PW>(a, piv, 0, sol, c.g, c.gm, c.ws); return; }
+#endif
+        GJ::extract(a, piv, 0, sol, c.gm);
+    }
+
     // Solve to (r_tol, κ_tol); z holds the initial point on entry and the final iterate on return (replicated in every lane).
     OD_HD static int solve(const Ctx& c, double* z, const double* th, double r_tol, double kappa_tol, int max_iter, int max_ls, double ls_scale, int* iters) {
         typedef DenseIP<M> S;
@@ -97,7 +105,7 @@ struct DenseIPG {
             double dl[NZ];
             if (NCONE > 0) {
                 double da[NZ];
-                GJ::extract(a, piv, 0, da, c.gm);
+                affine(a, piv, da, c);
                 const double a_aff = S::step_length(z, da, 1.0);
                 const double mu = S::cone_dot(z, da, 0.0) * (1.0 / (NCONE > 0 ? NCONE : 1));
                 const double mu_aff = S::cone_dot(z, da, a_aff) * (1.0 / (NCONE > 0 ? NCONE : 1));
@@ -119,11 +127,16 @@ struct DenseIPG {
                 }
                 double xm[RPL];
                 GJ::mine(dl, xm, c.g);
+#if OD_EXTRACT_SMEM
+                if constexpr (PW >= GJ::CINV + 2) GJ::template solve_sm<PW>(a, piv, xm, dl, c.g, c.gm, c.ws);
+                else GJ::solve(a, piv, xm, dl, c.g, c.gm);
+#else
                 GJ::solve(a, piv, xm, dl, c.g, c.gm);
+#endif
                 const double viol = od_max(r_vio, k_vio);
                 alpha = S::step_length(z, dl, od_max(0.95, 1.0 - viol * viol));
             } else {
-                GJ::extract(a, piv, 0, dl, c.gm);
+                affine(a, piv, dl, c);
                 alpha = 1.0;
             }
 #pragma unroll
