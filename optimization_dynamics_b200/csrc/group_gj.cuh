@@ -153,6 +153,9 @@ struct GroupGJ {
     template <int PITCH>
     OD_HD static bool factor_sm(double (&a)[RPL][NCOL], int (&piv)[NR], const int g, const unsigned gm, double* S) {
         static_assert(PITCH % 2 == 0 && PITCH >= NCOL + (NCOL % 2), "pairs of columns are moved as 16-byte words");
+        // OD_EXTRACT_SMEM with room for the two spare columns: inverse pivots go to the mirror, and column k of a pivot row keeps a
+        // ZERO multiplier instead of 1/pivot, so that solve_sm() needs no pivot-row predicate at all
+        constexpr bool MIRROR = OD_EXTRACT_SMEM && (PITCH >= CINV + 2);
         bool ok = true;
         unsigned done = 0;
 #pragma unroll
@@ -167,7 +170,14 @@ struct GroupGJ {
                     if (!((done >> s) & 1u)) {                 // padding rows and former pivot rows are never read again
                         double2* dst = reinterpret_cast<double2*>(S + r * PITCH + j0);
 #pragma unroll
+#if OD_EXTRACT_SMEM
+                        for (int j = j0; j < NCOL; j += 2) {
+                            if (j + 1 >= NCOL) S[r * PITCH + j] = a[s][j];                            // odd last column: 8-byte store, no zero pad
+                            else dst[(j - j0) / 2] = make_double2(a[s][j], a[s][j + 1]);
+                        }
+#else
                         for (int j = j0; j < NCOL; j += 2) dst[(j - j0) / 2] = make_double2(a[s][j], (j + 1 < NCOL) ? a[s][j + 1] : 0.0);
+#endif
                     }
                 }
             }
@@ -189,19 +199,31 @@ struct GroupGJ {
 #ifdef __CUDA_ARCH__
             if (G > 1 && k > 0) __syncwarp(gm);               // (the reduction above is not a memory barrier)
 #endif
-            if (OD_EXTRACT_SMEM && PITCH >= CINV + 2) S[pr * PITCH + CINV] = inv;      // every lane stores the same value: no barrier needed to read it back
+            if (MIRROR) S[pr * PITCH + CINV] = inv;              // every lane stores the same value: no barrier needed to read it back
             double prow[NCOL + 1];
             {
                 const double2* src = reinterpret_cast<const double2*>(S + pr * PITCH + j0);
 #pragma unroll
+#if OD_EXTRACT_SMEM
+                for (int j = j0; j < NCOL; j += 2) {
+                    if (j + 1 >= NCOL) { prow[j] = S[pr * PITCH + j]; prow[j + 1] = 0.0; }
+                    else { const double2 v = src[(j - j0) / 2]; prow[j] = v.x; prow[j + 1] = v.y; }
+                }
+#else
                 for (int j = j0; j < NCOL; j += 2) { const double2 v = src[(j - j0) / 2]; prow[j] = v.x; prow[j + 1] = v.y; }
+#endif
             }
 #pragma unroll
             for (int s = 0; s < RPL; ++s) {
                 const bool isp = own && (s == ws);
                 const double m = a[s][k] * inv;
+#if OD_EXTRACT_SMEM
+                const double me = isp ? 0.0 : m;
+                a[s][k] = MIRROR ? me : (isp ? inv : m);
+#else
                 a[s][k] = isp ? inv : m;
                 const double me = isp ? 0.0 : m;
+#endif
 #pragma unroll
                 for (int j = k + 1; j < NCOL; ++j) a[s][j] -= me * prow[j];
             }
@@ -245,17 +267,13 @@ struct GroupGJ {
     }
     template <int PITCH>
     OD_HD static void solve_sm(const double (&a)[RPL][NCOL], const int (&piv)[NR], double (&x)[RPL], double* sol, const int g, const unsigned gm, double* S) {
+        static_assert(OD_EXTRACT_SMEM && PITCH >= CINV + 2, "needs the factorisation of factor_sm in mirror mode (zero multiplier in pivot rows)");
 #pragma unroll
         for (int k = 0; k < NR; ++k) {
             const int wl = piv[k] & (G - 1), ws = piv[k] >> LG;
             const double xp = Grp<G>::bcast(pickv(x, ws), wl, gm);
-            const bool own = (g == wl);
 #pragma unroll
-            for (int s = 0; s < RPL; ++s) {
-                const bool isp = own && (s == ws);
-                const double me = isp ? 0.0 : a[s][k];
-                x[s] -= me * xp;
-            }
+            for (int s = 0; s < RPL; ++s) x[s] -= a[s][k] * xp;        // the pivot row of step k holds a zero in column k
         }
         gather_sm<PITCH>(x, piv, sol, g, gm, S);
     }
