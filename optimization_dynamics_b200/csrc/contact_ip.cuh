@@ -150,6 +150,8 @@ struct ContactIP {
         OD_HD void sync() const {
 #ifdef __CUDA_ARCH__
             if (G > 1) __syncwarp(gmask);
+#else
+            if (G > 1) host_team_sync();
 #endif
         }
     };
@@ -869,6 +871,7 @@ OD_HD bool warp_any(bool p) {
 #ifdef __CUDA_ARCH__
     return __any_sync(0xffffffffu, p);
 #else
+    if (HostLaneTeam* t = host_lane_team()) return t->any(p);
     return p;
 #endif
 }
@@ -1171,6 +1174,8 @@ OD_HD void contact_rollout_one(const RolloutArgs& ra, const int r, double* ws, c
         for (int e = g; e < NQ; e += G) Xr[(size_t)(t + 1) * NX + e] = Xr[(size_t)t * NX + NQ + e];
 #ifdef __CUDA_ARCH__
         __syncwarp(gmask);
+#else
+        host_team_sync();
 #endif
         contact_step_one<M, G, PPB, REG>(a, t, ws, g, gmask);
     }

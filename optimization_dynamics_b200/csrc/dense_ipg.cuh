@@ -24,6 +24,8 @@ struct DenseIPG {
     OD_HD static void sync() {
 #ifdef __CUDA_ARCH__
         if (G > 1) __syncwarp();
+#else
+        if (G > 1) host_team_sync();
 #endif
     }
 

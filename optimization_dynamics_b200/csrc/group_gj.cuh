@@ -39,6 +39,25 @@
 
 namespace od {
 
+// Host tier only (tests/host_check.cu): a team of lock-stepped host threads can stand in for the lanes of a warp.  When one is
+// installed for the calling thread, the G > 1 collectives below exchange real values between the threads, so the multi-lane code
+// paths (row distribution, pivot search, shared-memory mirror, warp votes) run on the CPU exactly as written.  Without a team
+// (the default, and always in liboptdyn_b200.so, which never runs these templates on the host) they are the G = 1 identities.
+struct HostLaneTeam {
+    int lane = 0;                                        // this thread's lane index within the emulated warp
+    virtual ~HostLaneTeam() {}
+    virtual double shfl_f64(double v, int src_lane) = 0;
+    virtual unsigned shfl_u32(unsigned v, int src_lane) = 0;
+    virtual bool any(bool p) = 0;
+    virtual void sync() = 0;
+};
+inline HostLaneTeam*& host_lane_team() { static thread_local HostLaneTeam* t = nullptr; return t; }
+OD_HD void host_team_sync() {
+#ifndef __CUDA_ARCH__
+    if (HostLaneTeam* t = host_lane_team()) t->sync();
+#endif
+}
+
 template <int G> struct Grp {
     static constexpr int LG = (G == 1 ? 0 : G == 2 ? 1 : G == 4 ? 2 : G == 8 ? 3 : G == 16 ? 4 : 5);
     static_assert((1 << LG) == G, "lanes per problem must be a power of two");
@@ -46,6 +65,8 @@ template <int G> struct Grp {
     OD_HD static double bcast(double v, int src, unsigned m) {
 #ifdef __CUDA_ARCH__
         if (G > 1) return __shfl_sync(m, v, src, G);
+#else
+        if (G > 1) if (HostLaneTeam* t = host_lane_team()) return t->shfl_f64(v, (t->lane & ~(G - 1)) + src);
 #endif
         return v;
     }
@@ -53,6 +74,9 @@ template <int G> struct Grp {
 #ifdef __CUDA_ARCH__
 #pragma unroll
         for (int d = 1; d < G; d <<= 1) { const unsigned o = __shfl_xor_sync(m, v, d, G); v = o > v ? o : v; }
+#else
+        if (HostLaneTeam* t = host_lane_team())
+            for (int d = 1; d < G; d <<= 1) { const unsigned o = t->shfl_u32(v, t->lane ^ d); v = o > v ? o : v; }
 #endif
         return v;
     }
@@ -198,6 +222,8 @@ struct GroupGJ {
             if (own) done |= 1u << ws;
 #ifdef __CUDA_ARCH__
             if (G > 1 && k > 0) __syncwarp(gm);               // (the reduction above is not a memory barrier)
+#else
+            if (G > 1 && k > 0) host_team_sync();
 #endif
             if (MIRROR) S[pr * PITCH + CINV] = inv;              // every lane stores the same value: no barrier needed to read it back
             double prow[NCOL + 1];
@@ -246,6 +272,8 @@ struct GroupGJ {
     OD_HD static void gather_sm(const double (&y)[RPL], const int (&piv)[NR], double* sol, const int g, const unsigned gm, double* S) {
 #ifdef __CUDA_ARCH__
         if (G > 1) __syncwarp(gm);                                // earlier readers of column CSOL are done
+#else
+        if (G > 1) host_team_sync();
 #endif
 #pragma unroll
         for (int s = 0; s < RPL; ++s) {
@@ -254,6 +282,8 @@ struct GroupGJ {
         }
 #ifdef __CUDA_ARCH__
         if (G > 1) __syncwarp(gm);
+#else
+        if (G > 1) host_team_sync();
 #endif
 #pragma unroll
         for (int k = 0; k < NR; ++k) sol[k] = S[piv[k] * PITCH + CSOL];

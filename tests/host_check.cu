@@ -4,13 +4,65 @@
 // container without a GPU) can check the condensed-Newton algebra against the oracle before any GPU time is spent.
 // Built by tests/conftest.py with:  nvcc -O2 -std=c++17 -Xcompiler -fPIC -shared -o tests/_build/libhostcheck.so tests/host_check.cu
 #include <string.h>
+#include <stdint.h>
 #include "../optimization_dynamics_b200/csrc/rocket.cuh"
 #include "../optimization_dynamics_b200/csrc/riccati.cuh"
 #include <vector>
 
 using namespace od;
 
+// ---- lane team: T host threads in lockstep stand in for the lanes of one warp (HostLaneTeam, csrc/group_gj.cuh) ---------------
+#include <pthread.h>
+#include <thread>
+struct TeamShared {
+    int T; pthread_barrier_t bar; double bufd[32]; unsigned bufu[32]; int bufp[32];
+    explicit TeamShared(int t) : T(t) { pthread_barrier_init(&bar, nullptr, (unsigned)t); }
+    ~TeamShared() { pthread_barrier_destroy(&bar); }
+    void wait() { pthread_barrier_wait(&bar); }
+};
+struct LaneView : HostLaneTeam {
+    TeamShared* S;
+    double shfl_f64(double v, int src) override { S->bufd[lane] = v; S->wait(); const double r = S->bufd[src]; S->wait(); return r; }
+    unsigned shfl_u32(unsigned v, int src) override { S->bufu[lane] = v; S->wait(); const unsigned r = S->bufu[src]; S->wait(); return r; }
+    bool any(bool p) override { S->bufp[lane] = p ? 1 : 0; S->wait(); int r = 0; for (int l = 0; l < S->T; ++l) r |= S->bufp[l]; S->wait(); return r != 0; }
+    void sync() override { S->wait(); }
+};
+// Runs fn(lane) on T lock-stepped threads with a lane team installed (every thread must make the same sequence of collective calls,
+// which is what the warp-synchronous design of the kernels guarantees).
+template <class F> static void run_team(int T, F fn) {
+    TeamShared sh(T);
+    std::vector<std::thread> th;
+    for (int lane = 0; lane < T; ++lane)
+        th.emplace_back([&sh, lane, &fn]() {
+            LaneView v; v.S = &sh; v.lane = lane;
+            host_lane_team() = &v;
+            fn(lane);
+            host_lane_team() = nullptr;
+        });
+    for (auto& t : th) t.join();
+}
+// The register path with G lanes per problem: one emulated warp (32 lanes = 32/G problems) after the other, exactly the index
+// arithmetic of contact_step_kernel (padding lanes of the last warp repeat the last problem).
+template <class M, int G> static void run_contact_lanes(const StepArgs& a) {
+    constexpr int PPB = 32 / G;
+    typedef ContactIP<M, G, PPB, true> IP;
+    std::vector<double> ws((size_t)PPB * IP::WS_SLOT + 2);
+    double* base = ws.data(); if (reinterpret_cast<uintptr_t>(base) & 15) ++base;        // 16-byte aligned like dynamic shared memory
+    const int nwarps = (a.B + PPB - 1) / PPB;
+    for (int w = 0; w < nwarps; ++w)
+        run_team(32, [&](int lane) {
+            const int slot = lane / G, g = lane % G;
+            int i = w * PPB + slot; if (i >= a.B) i = a.B - 1;
+            contact_step_one<M, G, PPB, true>(a, i, base + slot * IP::WS_SLOT, g, 0xffffffffu);
+        });
+}
+
 template <class M> static void run_contact(const StepArgs& a, int reg) {
+    if constexpr (M::NC + M::NP > 0) {           // cone models have the cooperative register path: reg = 4 / 8 / 16 selects the lane count
+        if (reg == 4) { run_contact_lanes<M, 4>(a); return; }
+        if (reg == 8) { run_contact_lanes<M, 8>(a); return; }
+        if (reg == 16) { run_contact_lanes<M, 16>(a); return; }
+    }
     if (reg) {   // register-path algebra (group_gj.cuh) with one lane: shuffles are identities, the Gauss–Jordan arithmetic is the same
         alignas(16) double ws[ContactIP<M, 1, 1, true>::WS];
         for (int i = 0; i < a.B; ++i) contact_step_one<M, 1, 1, true>(a, i, ws, 0, 0u);

@@ -13,14 +13,15 @@ DIMS = {"acrobot_impact": (2, 1), "acrobot_nominal": (2, 1), "cartpole_friction"
         "planar_push": (5, 2), "hopper": (4, 2)}
 
 
-def build():
-    so = os.path.join(_HERE, "_build", "libhostcheck.so")
+def build(flags=(), tag=""):
+    """flags: extra -D… switches of the kernels' prepared variants (built as a separate library, tag = its file-name suffix)."""
+    so = os.path.join(_HERE, "_build", "libhostcheck%s.so" % tag)
     csrc = os.path.join(_ROOT, "optimization_dynamics_b200", "csrc")
     srcs = [os.path.join(_HERE, "host_check.cu")] + [os.path.join(dp, f) for dp, _, fs in os.walk(csrc) for f in fs]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         os.makedirs(os.path.dirname(so), exist_ok=True)
-        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC", "-shared", "-o", so,
-                               os.path.join(_HERE, "host_check.cu")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC", "-shared"] + list(flags) +
+                              ["-o", so, os.path.join(_HERE, "host_check.cu")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     return so
 
 
@@ -31,11 +32,30 @@ def lib():
     return _LIB
 
 
+class use_variant:
+    """with use_variant(["-DOD_EXTRACT_SMEM=1"], "_extract"): …   — the calls inside run a differently built copy of the templates."""
+
+    def __init__(self, flags, tag):
+        self.flags, self.tag = flags, tag
+
+    def __enter__(self):
+        global _LIB
+        self.saved = _LIB
+        _LIB = C.CDLL(build(self.flags, self.tag))
+        return self
+
+    def __exit__(self, *exc):
+        global _LIB
+        _LIB = self.saved
+
+
 def _p(a, t=C.c_double):
     return None if a is None else a.ctypes.data_as(C.POINTER(t))
 
 
 def step(model, q1, q2, u, h, k_eval=1e-4, k_grad=1e-3, fric=None, want_eval=True, want_grad=True, eta=None, r_tol=1e-8, reg=False):
+    """reg: False = shared-memory-LU templates, True / 1 = register path with one lane, 4 / 8 / 16 = register path with that many
+    cooperating lanes per problem, run by a team of 32 lock-stepped host threads per emulated warp (cone models only)."""
     nq, nu = DIMS[model]
     q1 = np.ascontiguousarray(q1, dtype=np.float64).reshape(-1, nq); B0 = q1.shape[0]
     q2 = np.ascontiguousarray(q2, dtype=np.float64).reshape(B0, nq)

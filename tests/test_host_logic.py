@@ -245,3 +245,41 @@ def test_generated_model_code_is_up_to_date(tmp_path):
         assert open(os.path.join(gen_dir, f)).read() == open(os.path.join(str(tmp_path), f)).read(), f
     pp = open(os.path.join(gen_dir, "model_planar_push.cuh")).read()
     assert pp.count("pow(") == 1 and "ipow<" in pp            # one tenth root per evaluation point, integer powers by squaring
+
+
+@pytest.mark.parametrize("name,lanes,B", [("hopper", 8, 22), ("hopper", 4, 13), ("hopper", 16, 5), ("cartpole_friction", 4, 19),
+                                          ("acrobot_impact", 4, 11), ("planar_push", 8, 6)])
+def test_cooperative_lanes_on_the_host_match_one_lane(name, lanes, B):
+    """The multi-lane register path (rows spread over the lanes of a group, pivot search by shuffles, pivot rows through the
+    shared-memory mirror, warp votes of the lock-stepped state machine) run on the CPU by a team of 32 host threads per emulated
+    warp (HostLaneTeam, csrc/group_gj.cuh): identical results to the one-lane run of the same templates — partial last warps,
+    problems of one warp finishing at different iterations and the rank-revealing IFT of the planar push included — and parity
+    with the oracle."""
+    gen, h, ke, kg, fric, _ = CONFIGS[name]
+    q1, q2, u = gen(B, h=h, seed=11)
+    one = H.step(name, q1, q2, u, h, ke, kg, fric=fric, reg=1)
+    many = H.step(name, q1, q2, u, h, ke, kg, fric=fric, reg=lanes)
+    assert np.array_equal(one["status"], many["status"]) and np.array_equal(one["it_eval"], many["it_eval"])
+    ok = one["status"] == 0
+    assert ok.mean() > 0.8
+    for k in ("q3", "dq1", "dq2", "du"):
+        assert np.array_equal(one[k][ok], many[k][ok]), k
+    e, g = oracle_pair(O, name, q1, q2, u)
+    good = ok & (e["status"] == 0) & (g["status"] == 0) & (e["margin"] > 1e-6) & (g["margin"] > 1e-6) & (e["iters"] <= 30)
+    assert np.abs(many["q3"] - e["q3"])[good].max() < 1e-8
+
+
+@pytest.mark.parametrize("name,lanes,B", [("hopper", 8, 22), ("hopper", 4, 13), ("cartpole_friction", 4, 19), ("acrobot_impact", 4, 11)])
+def test_prepared_mirror_variant_matches_shipped_path(name, lanes, B):
+    """-DOD_EXTRACT_SMEM=1 (inverse pivots and solutions through the shared-memory mirror, zero multiplier in pivot
+    rows; prepared, not the shipped default) must reproduce the shipped path bit for bit — one lane and cooperative lanes."""
+    gen, h, ke, kg, fric, _ = CONFIGS[name]
+    q1, q2, u = gen(B, h=h, seed=12)
+    base = H.step(name, q1, q2, u, h, ke, kg, fric=fric, reg=lanes)
+    with H.use_variant(["-DOD_EXTRACT_SMEM=1"], "_extract"):
+        var1 = H.step(name, q1, q2, u, h, ke, kg, fric=fric, reg=1)
+        var = H.step(name, q1, q2, u, h, ke, kg, fric=fric, reg=lanes)
+    for other in (var1, var):
+        assert np.array_equal(base["status"], other["status"]) and np.array_equal(base["it_eval"], other["it_eval"])
+        for k in ("q3", "dq1", "dq2", "du"):
+            assert np.array_equal(base[k], other[k], equal_nan=True), k
