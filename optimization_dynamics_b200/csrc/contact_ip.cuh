@@ -205,7 +205,10 @@ struct ContactIP {
             for (int i = 0; i < NR; ++i) L.S(i, NR) = x[i];
             L.sync();
             fetch_rows<NR + 1>(L, L.a);
-#if OD_GJ_SMEM
+#if OD_GJ_SMEM && OD_EXTRACT_SMEM
+            if constexpr (PW >= GJ::CINV + 2) L.ok = GJ::template factor_v2<PW>(L.a, L.piv, L.g, L.gmask, &L.S(0, 0));
+            else L.ok = GJ::template factor_sm<PW>(L.a, L.piv, L.g, L.gmask, &L.S(0, 0));
+#elif OD_GJ_SMEM
             L.ok = GJ::template factor_sm<PW>(L.a, L.piv, L.g, L.gmask, &L.S(0, 0));
 #else
             L.ok = GJ::factor(L.a, L.piv, L.g, L.gmask);

@@ -102,7 +102,13 @@ struct DenseIPG {
             double a[RPL][NZ + 1];
             int piv[NZ];
             fetch_rows<NZ + 1>(c, a);
+#if OD_EXTRACT_SMEM
+            bool ok;
+            if constexpr (PW >= GJ::CINV + 2) ok = GJ::template factor_v2<PW>(a, piv, c.g, c.gm, c.ws);
+            else ok = GJ::template factor_sm<PW>(a, piv, c.g, c.gm, c.ws);
+#else
             const bool ok = GJ::template factor_sm<PW>(a, piv, c.g, c.gm, c.ws);     // pivot rows through the staging area (group_gj.cuh)
+#endif
             if (active && !ok) { status = ST_FAIL; active = false; }
             double dl[NZ];
             if (NCONE > 0) {

@@ -177,9 +177,6 @@ struct GroupGJ {
     template <int PITCH>
     OD_HD static bool factor_sm(double (&a)[RPL][NCOL], int (&piv)[NR], const int g, const unsigned gm, double* S) {
         static_assert(PITCH % 2 == 0 && PITCH >= NCOL + (NCOL % 2), "pairs of columns are moved as 16-byte words");
-        // OD_EXTRACT_SMEM with room for the two spare columns: inverse pivots go to the mirror, and column k of a pivot row keeps a
-        // ZERO multiplier instead of 1/pivot, so that solve_sm() needs no pivot-row predicate at all
-        constexpr bool MIRROR = OD_EXTRACT_SMEM && (PITCH >= CINV + 2);
         bool ok = true;
         unsigned done = 0;
 #pragma unroll
@@ -194,14 +191,7 @@ struct GroupGJ {
                     if (!((done >> s) & 1u)) {                 // padding rows and former pivot rows are never read again
                         double2* dst = reinterpret_cast<double2*>(S + r * PITCH + j0);
 #pragma unroll
-#if OD_EXTRACT_SMEM
-                        for (int j = j0; j < NCOL; j += 2) {
-                            if (j + 1 >= NCOL) S[r * PITCH + j] = a[s][j];                            // odd last column: 8-byte store, no zero pad
-                            else dst[(j - j0) / 2] = make_double2(a[s][j], a[s][j + 1]);
-                        }
-#else
                         for (int j = j0; j < NCOL; j += 2) dst[(j - j0) / 2] = make_double2(a[s][j], (j + 1 < NCOL) ? a[s][j + 1] : 0.0);
-#endif
                     }
                 }
             }
@@ -225,31 +215,89 @@ struct GroupGJ {
 #else
             if (G > 1 && k > 0) host_team_sync();
 #endif
-            if (MIRROR) S[pr * PITCH + CINV] = inv;              // every lane stores the same value: no barrier needed to read it back
             double prow[NCOL + 1];
             {
                 const double2* src = reinterpret_cast<const double2*>(S + pr * PITCH + j0);
 #pragma unroll
-#if OD_EXTRACT_SMEM
-                for (int j = j0; j < NCOL; j += 2) {
-                    if (j + 1 >= NCOL) { prow[j] = S[pr * PITCH + j]; prow[j + 1] = 0.0; }
-                    else { const double2 v = src[(j - j0) / 2]; prow[j] = v.x; prow[j + 1] = v.y; }
-                }
-#else
                 for (int j = j0; j < NCOL; j += 2) { const double2 v = src[(j - j0) / 2]; prow[j] = v.x; prow[j + 1] = v.y; }
-#endif
             }
 #pragma unroll
             for (int s = 0; s < RPL; ++s) {
                 const bool isp = own && (s == ws);
                 const double m = a[s][k] * inv;
-#if OD_EXTRACT_SMEM
-                const double me = isp ? 0.0 : m;
-                a[s][k] = MIRROR ? me : (isp ? inv : m);
-#else
                 a[s][k] = isp ? inv : m;
                 const double me = isp ? 0.0 : m;
+#pragma unroll
+                for (int j = k + 1; j < NCOL; ++j) a[s][j] -= me * prow[j];
+            }
+        }
+        return ok;
+    }
+
+    // Prepared variant of factor_sm() (-DOD_EXTRACT_SMEM=1; needs two spare mirror columns, PITCH ≥ CINV + 2):
+    //   * the inverse pivot of step k goes to S[pivot row][CINV] and column k of the pivot row keeps a ZERO multiplier, so that
+    //     solve_sm() needs no pivot-row predicate and extract_sm() / solve_sm() scale and gather through the mirror;
+    //   * an odd last column is moved as 8 bytes (no zero pad to materialise);
+    //   * a lane recognises its pivot row by comparing the winning row index with its own row numbers, and keeps one "still a
+    //     candidate" flag per slot — no lane / slot decoding of the winner beyond the source lane of the reciprocal.
+    // Same arithmetic, in the same order, as factor_sm().
+    template <int PITCH>
+    OD_HD static bool factor_v2(double (&a)[RPL][NCOL], int (&piv)[NR], const int g, const unsigned gm, double* S) {
+        static_assert(PITCH % 2 == 0 && PITCH >= CINV + 2, "two spare columns behind the (padded) matrix");
+        bool ok = true;
+        bool cand[RPL];                                            // slot can still become a pivot row (not padding, not used yet)
+#pragma unroll
+        for (int s = 0; s < RPL; ++s) cand[s] = (s * G + g < NR);
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+            const int j0 = (k + 1) & ~1;
+            if (k > 0) {
+#pragma unroll
+                for (int s = 0; s < RPL; ++s) {
+                    if (cand[s]) {
+                        double* row = S + (s * G + g) * PITCH;
+#pragma unroll
+                        for (int j = j0; j < NCOL; j += 2) {
+                            if (j + 1 >= NCOL) row[j] = a[s][j];
+                            else *reinterpret_cast<double2*>(row + j) = make_double2(a[s][j], a[s][j + 1]);
+                        }
+                    }
+                }
+            }
+            unsigned key = 0;
+            double best = a[0][k];                                 // this lane's best candidate (value of the slot that carries `key`)
+#pragma unroll
+            for (int s = 0; s < RPL; ++s) {
+                const unsigned ks = cand[s] ? ((abs_hi32(a[s][k]) & ~31u) | (unsigned)(s * G + g)) : 0u;
+                if (s > 0) best = (ks > key) ? a[s][k] : best;
+                key = ks > key ? ks : key;
+            }
+            const double myinv = pivot_rcp(best);
+            key = Grp<G>::umax_all(key, gm);
+            ok = ok && (key >= 32u) && (key < 0x7ff00000u);
+            const int pr = (int)(key & 31u);
+            piv[k] = pr;
+            const double inv = Grp<G>::bcast(myinv, pr & (G - 1), gm);
+#ifdef __CUDA_ARCH__
+            if (G > 1 && k > 0) __syncwarp(gm);
+#else
+            if (G > 1 && k > 0) host_team_sync();
 #endif
+            const double* prow_s = S + pr * PITCH;
+            S[pr * PITCH + CINV] = inv;                            // every lane stores the same value: its owner reads it back without a barrier
+            double prow[NCOL + 1];
+#pragma unroll
+            for (int j = j0; j < NCOL; j += 2) {
+                if (j + 1 >= NCOL) { prow[j] = prow_s[j]; prow[j + 1] = 0.0; }
+                else { const double2 v = *reinterpret_cast<const double2*>(prow_s + j); prow[j] = v.x; prow[j + 1] = v.y; }
+            }
+#pragma unroll
+            for (int s = 0; s < RPL; ++s) {
+                const bool isp = (pr == s * G + g);
+                cand[s] = cand[s] && !isp;
+                const double m = a[s][k] * inv;
+                const double me = isp ? 0.0 : m;
+                a[s][k] = me;
 #pragma unroll
                 for (int j = k + 1; j < NCOL; ++j) a[s][j] -= me * prow[j];
             }
@@ -266,7 +314,7 @@ struct GroupGJ {
         }
     }
 
-    // OD_EXTRACT_SMEM variants.  Row r's inverse pivot sits in S[r·PITCH + CINV] (factor_sm); every lane scales its own rows,
+    // OD_EXTRACT_SMEM variants.  Row r's inverse pivot sits in S[r·PITCH + CINV] (factor_v2); every lane scales its own rows,
     // publishes them in column CSOL and reads unknown k from the row that was the pivot of step k.
     template <int PITCH>
     OD_HD static void gather_sm(const double (&y)[RPL], const int (&piv)[NR], double* sol, const int g, const unsigned gm, double* S) {
@@ -297,7 +345,7 @@ struct GroupGJ {
     }
     template <int PITCH>
     OD_HD static void solve_sm(const double (&a)[RPL][NCOL], const int (&piv)[NR], double (&x)[RPL], double* sol, const int g, const unsigned gm, double* S) {
-        static_assert(OD_EXTRACT_SMEM && PITCH >= CINV + 2, "needs the factorisation of factor_sm in mirror mode (zero multiplier in pivot rows)");
+        static_assert(OD_EXTRACT_SMEM && PITCH >= CINV + 2, "needs the factorisation of factor_v2 (zero multiplier in pivot rows, inverse pivots in the mirror)");
 #pragma unroll
         for (int k = 0; k < NR; ++k) {
             const int wl = piv[k] & (G - 1), ws = piv[k] >> LG;
