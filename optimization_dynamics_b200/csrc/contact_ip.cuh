@@ -1162,6 +1162,8 @@ OD_HD void contact_rollout_one(const RolloutArgs& ra, const int r, double* ws, c
     for (int t = 0; t < T - 1; ++t) {
 #ifdef __CUDA_ARCH__
         __syncwarp(gmask);                                     // x_t (written by other lanes) is visible
+#else
+        host_team_sync();
 #endif
         for (int e = g; e < NU; e += G) {
             double u = ub[(size_t)t * NU + e];

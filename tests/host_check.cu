@@ -94,7 +94,24 @@ extern "C" int hc_contact_step(int model, int B, const double* q1, const double*
     return 0;
 }
 
+template <class M, int G> static void run_rollout_lanes(const RolloutArgs& a) {
+    constexpr int PPB = 32 / G;
+    typedef ContactIP<M, G, PPB, true> IP;
+    std::vector<double> ws((size_t)PPB * IP::WS_SLOT + 2);
+    double* base = ws.data(); if (reinterpret_cast<uintptr_t>(base) & 15) ++base;
+    const int nwarps = (a.R + PPB - 1) / PPB;
+    for (int w = 0; w < nwarps; ++w)
+        run_team(32, [&](int lane) {
+            const int slot = lane / G, g = lane % G;
+            int r = w * PPB + slot; if (r >= a.R) r = a.R - 1;
+            contact_rollout_one<M, G, PPB, true>(a, r, base + slot * IP::WS_SLOT, g, 0xffffffffu);
+        });
+}
 template <class M> static void run_rollout(const RolloutArgs& a, int reg) {
+    if constexpr (M::NC + M::NP > 0) {
+        if (reg == 4) { run_rollout_lanes<M, 4>(a); return; }
+        if (reg == 8) { run_rollout_lanes<M, 8>(a); return; }
+    }
     if (reg) { alignas(16) double ws[ContactIP<M, 1, 1, true>::WS]; for (int r = 0; r < a.R; ++r) contact_rollout_one<M, 1, 1, true>(a, r, ws, 0, 0u); }
     else { alignas(16) double ws[ContactIP<M>::WS]; for (int r = 0; r < a.R; ++r) contact_rollout_one<M, 1, 1, false>(a, r, ws, 0, 0u); }
 }
@@ -128,13 +145,29 @@ extern "C" int hc_riccati(int NT, int T, int nq, int nu, const double* jac, cons
     return 0;
 }
 
+// rocket_kernel_g with G lanes per problem on emulated warps (same index arithmetic as the kernel)
+template <int G> static void run_rocket_lanes(const RocketArgs& a) {
+    constexpr int PPB = 32 / G;
+    std::vector<double> ws((size_t)PPB * RocketG<G>::WS + 2);
+    double* base = ws.data(); if (reinterpret_cast<uintptr_t>(base) & 15) ++base;
+    const int nwarps = (a.B + PPB - 1) / PPB;
+    for (int w = 0; w < nwarps; ++w)
+        run_team(32, [&](int lane) {
+            const int slot = lane / G, g = lane % G;
+            int i = w * PPB + slot; if (i >= a.B) i = a.B - 1;
+            RocketG<G>::run(a, i, base + slot * RocketG<G>::WS, g);
+        });
+}
+
 extern "C" int hc_rocket(int B, const double* x, const double* u, double h, double u_max, int proj, int want_grad, int proj_only,
                          double* y, double* dx, double* du, double* uproj, double* duproj, int* status, int* iters, int reg) {
     RocketArgs a; memset(&a, 0, sizeof(a));
     a.B = B; a.x = x; a.u = u; a.y = y; a.dx = dx; a.du = du; a.uproj = uproj; a.duproj = duproj; a.status = status; a.iters = iters;
     a.h = h; a.u_max = u_max; a.proj = proj; a.want_grad = want_grad; a.proj_only = proj_only;
     a.opts.r_tol = 1e-8; a.opts.kappa_eval_tol = 1e-4; a.opts.kappa_grad_tol = 1e-4; a.opts.ls_scale = 0.5; a.opts.max_iter = 100; a.opts.max_ls = 25;
-    if (reg) { alignas(16) double ws[RocketG<1>::WS]; for (int i = 0; i < B; ++i) RocketG<1>::run(a, i, ws, 0); }
+    if (reg == 4) run_rocket_lanes<4>(a);
+    else if (reg == 8) run_rocket_lanes<8>(a);
+    else if (reg) { alignas(16) double ws[RocketG<1>::WS]; for (int i = 0; i < B; ++i) RocketG<1>::run(a, i, ws, 0); }
     else for (int i = 0; i < B; ++i) rocket_one(a, i);
     return 0;
 }

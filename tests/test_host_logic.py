@@ -283,3 +283,26 @@ def test_prepared_mirror_variant_matches_shipped_path(name, lanes, B):
         assert np.array_equal(base["status"], other["status"]) and np.array_equal(base["it_eval"], other["it_eval"])
         for k in ("q3", "dq1", "dq2", "du"):
             assert np.array_equal(base[k], other[k], equal_nan=True), k
+
+
+@pytest.mark.parametrize("variant", [None, "-DOD_EXTRACT_SMEM=1"])
+def test_cooperative_lanes_rocket_and_rollouts_on_the_host(variant):
+    """rocket_kernel_g (dense 12×12 dynamics + 10×10 cone projection + chain rule) and the closed-loop rollout template with
+    cooperating lanes on emulated warps: identical to their one-lane runs, for the shipped path and the prepared variant."""
+    import contextlib
+    ctx = H.use_variant([variant], "_extract") if variant else contextlib.nullcontext()
+    x, u = W.rocket_batch(9, seed=4)
+    q1, q2, _ = W.hopper_batch(6, h=0.05, seed=5)
+    x1 = np.concatenate([q1, q2], axis=1)
+    ubar = np.tile(np.array([0.0, 9.81 * 3.0 * 0.5 * 0.05]), (6, 4, 1)) + 0.1 * np.random.default_rng(6).standard_normal((6, 4, 2))
+    with ctx:
+        for proj in (False, True):
+            one = H.rocket(x, u, 0.05, 12.5, proj, reg=1)
+            for lanes in (8, 4):
+                many = H.rocket(x, u, 0.05, 12.5, proj, reg=lanes)
+                assert np.array_equal(one["status"], many["status"]) and np.array_equal(one["iters"], many["iters"])
+                for k in ("y", "dx", "du", "uproj", "duproj"):
+                    assert np.array_equal(one[k], many[k]), (proj, lanes, k)
+        X1, U1, s1 = H.rollout("hopper", x1, ubar, 0.05, reg=1)
+        X8, U8, s8 = H.rollout("hopper", x1, ubar, 0.05, reg=8)
+        assert np.array_equal(s1, s8) and np.array_equal(X1, X8) and np.array_equal(U1, U8)
