@@ -306,3 +306,21 @@ def test_cooperative_lanes_rocket_and_rollouts_on_the_host(variant):
         X1, U1, s1 = H.rollout("hopper", x1, ubar, 0.05, reg=1)
         X8, U8, s8 = H.rollout("hopper", x1, ubar, 0.05, reg=8)
         assert np.array_equal(s1, s8) and np.array_equal(X1, X8) and np.array_equal(U1, U8)
+
+
+def test_pathological_inputs_agree_across_lanes_and_variants():
+    """NaN / inf / absurd inputs and problems that run into the iteration cap: same status, iteration counts and (NaN-aware)
+    outputs for one lane, eight emulated lanes, and the prepared variant — failures are reported, never hidden or hung."""
+    q1, q2, u = W.hopper_batch(8, h=0.05, seed=2)
+    q1[1, 0] = np.nan; u[2, :] = 1e12; q2[3, 1] = -50.0; q1[4, :] = q2[4, :]; u[5, :] = np.inf; q2[6, 3] = 1e-30
+    runs = [H.step("hopper", q1, q2, u, 0.05, reg=1), H.step("hopper", q1, q2, u, 0.05, reg=8)]
+    with H.use_variant(["-DOD_EXTRACT_SMEM=1"], "_extract"):
+        runs += [H.step("hopper", q1, q2, u, 0.05, reg=1), H.step("hopper", q1, q2, u, 0.05, reg=8)]
+    base = runs[0]
+    assert base["st_eval"][1] == 2 and base["st_eval"][5] == 2            # non-finite inputs: ST_FAIL
+    assert set(base["st_eval"][[2, 3]]) <= {1, 2}                          # absurd inputs: iteration cap or failure, reported
+    assert base["status"][0] == 0 and base["status"][4] == 0
+    for other in runs[1:]:
+        assert np.array_equal(base["status"], other["status"]) and np.array_equal(base["it_eval"], other["it_eval"])
+        for k in ("q3", "dq1", "dq2", "du"):
+            assert np.array_equal(base[k], other[k], equal_nan=True), k
