@@ -269,7 +269,8 @@ def test_cooperative_lanes_on_the_host_match_one_lane(name, lanes, B):
     assert np.abs(many["q3"] - e["q3"])[good].max() < 1e-8
 
 
-@pytest.mark.parametrize("name,lanes,B", [("hopper", 8, 22), ("hopper", 4, 13), ("cartpole_friction", 4, 19), ("acrobot_impact", 4, 11)])
+@pytest.mark.parametrize("name,lanes,B", [("hopper", 8, 22), ("hopper", 4, 13), ("hopper", 16, 5), ("cartpole_friction", 4, 19),
+                                          ("acrobot_impact", 4, 11), ("planar_push", 16, 4), ("planar_push", 8, 6)])
 def test_prepared_mirror_variant_matches_shipped_path(name, lanes, B):
     """-DOD_EXTRACT_SMEM=1 (inverse pivots and solutions through the shared-memory mirror, zero multiplier in pivot
     rows; prepared, not the shipped default) must reproduce the shipped path bit for bit — one lane and cooperative lanes."""
