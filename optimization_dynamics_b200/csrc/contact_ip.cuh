@@ -27,6 +27,10 @@
 #ifndef OD_GJ_SMEM
 #define OD_GJ_SMEM 1
 #endif
+// 1 (prepared, off): iterate advanced in place, see contact_step_one
+#ifndef OD_INPLACE_Z
+#define OD_INPLACE_Z 0
+#endif
 
 // Every solver routine is __host__ __device__ so that tests/host_check.cu can single-step the very same template code on the
 // CPU against the oracle (a debugging aid for a GPU-less build container; liboptdyn_b200.so exports no host compute path).
@@ -936,6 +940,9 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
     double trc[IP::NTC1], trv[IP::NTV1];            // sin/cos of the θ-only arguments (once) and of the q-dependent ones (per candidate)
     M::trig_const(th, trc);
     double r_vio = 0.0, k_vio = 0.0, alpha = 0.0;
+#if OD_INPLACE_Z
+    double step = 0.0;
+#endif
     D = z;                                  // any finite values: the first candidate uses alpha = 0
     bool first = true, eval_done = !a.want_eval, grad_done = !a.want_grad;
     bool active = true;                    // this problem is still iterating
@@ -943,6 +950,21 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
     for (;;) {
         // ---- candidate z − αΔ and its residual (the only residual call site) ----------------------------------------------
         typename IP::R rc; double rv2, kv2;
+#if OD_INPLACE_Z
+        // Prepared variant: the iterate is advanced in place, z ← z − step·Δ, and a rejected step is taken back by the
+        // difference of the step lengths — no second copy of the iterate, no copy on acceptance.  Identical arithmetic on the
+        // accepted path; a retried candidate (rare: no hopper / cartpole / acrobot problem of the test batches ever retries) is
+        // z − αΔ + (α − α')Δ instead of z − α'Δ, a rounding-level difference.
+        IP::candidate(z, D, step, z);
+        M::trig_var(z.q, th, trv);
+        IP::residual(z, th, trc, trv, rc, rv2, kv2);
+        const bool retry = active && !(first || rv2 <= r_vio || kv2 <= k_vio || ls >= a.opts.max_ls);
+        step = 0.0;                                                 // a problem that does not retry re-evaluates its unchanged candidate
+        if (retry) { const double a2 = alpha * a.opts.ls_scale; step = a2 - alpha; alpha = a2; ++ls; }
+        if (warp_any(retry)) continue;
+        if (active) {
+            r_vio = rv2; k_vio = kv2;
+#else
         IP::candidate(z, D, alpha, zc);
         M::trig_var(zc.q, th, trv);
         IP::residual(zc, th, trc, trv, rc, rv2, kv2);
@@ -951,6 +973,7 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
         if (warp_any(retry)) continue;                              // (the other problems of the warp re-evaluate their unchanged candidate)
         if (active) {
             z = zc; r_vio = rv2; k_vio = kv2;
+#endif
             if (!first) ++it;
             first = false;
             // ---- accepted iterate: termination tests ------------------------------------------------------------------------
@@ -985,6 +1008,9 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
         }
         IP::direction(L, z, rc, r_vio, k_vio, D, alpha);
         if (!active) alpha = 0.0;                                // a finished problem stays where it is
+#if OD_INPLACE_Z
+        step = alpha;
+#endif
         ls = 0;
     }
     // ---- IFT at the snapshot.  It sits after the loop on purpose: the problems of a warp converge at different iterations, and a

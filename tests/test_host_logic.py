@@ -271,22 +271,29 @@ def test_cooperative_lanes_on_the_host_match_one_lane(name, lanes, B):
 
 @pytest.mark.parametrize("name,lanes,B", [("hopper", 8, 22), ("hopper", 4, 13), ("hopper", 16, 5), ("cartpole_friction", 4, 19),
                                           ("acrobot_impact", 4, 11), ("planar_push", 16, 4), ("planar_push", 8, 6)])
-def test_prepared_mirror_variant_matches_shipped_path(name, lanes, B):
-    """-DOD_EXTRACT_SMEM=1 (inverse pivots and solutions through the shared-memory mirror, zero multiplier in pivot
-    rows; prepared, not the shipped default) must reproduce the shipped path bit for bit — one lane and cooperative lanes."""
+@pytest.mark.parametrize("flags,tag", [(["-DOD_EXTRACT_SMEM=1"], "_extract"), (["-DOD_EXTRACT_SMEM=1", "-DOD_INPLACE_Z=1"], "_v2z")])
+def test_prepared_mirror_variant_matches_shipped_path(name, lanes, B, flags, tag):
+    """The prepared, not shipped, variants of DESIGN.md §9 — -DOD_EXTRACT_SMEM=1 (inverse pivots and solutions through the
+    shared-memory mirror, zero multiplier in pivot rows) and on top of it -DOD_INPLACE_Z=1 (iterate advanced in place) — must
+    reproduce the shipped path bit for bit, with one lane and with cooperative lanes.  (The in-place variant differs by rounding
+    only on a retried line-search step, which these batches do not contain except, rarely, on the planar push.)"""
     gen, h, ke, kg, fric, _ = CONFIGS[name]
     q1, q2, u = gen(B, h=h, seed=12)
     base = H.step(name, q1, q2, u, h, ke, kg, fric=fric, reg=lanes)
-    with H.use_variant(["-DOD_EXTRACT_SMEM=1"], "_extract"):
+    with H.use_variant(flags, tag):
         var1 = H.step(name, q1, q2, u, h, ke, kg, fric=fric, reg=1)
         var = H.step(name, q1, q2, u, h, ke, kg, fric=fric, reg=lanes)
+    exact = not ("-DOD_INPLACE_Z=1" in flags and name == "planar_push")
     for other in (var1, var):
         assert np.array_equal(base["status"], other["status"]) and np.array_equal(base["it_eval"], other["it_eval"])
         for k in ("q3", "dq1", "dq2", "du"):
-            assert np.array_equal(base[k], other[k], equal_nan=True), k
+            if exact:
+                assert np.array_equal(base[k], other[k], equal_nan=True), k
+            else:
+                assert np.allclose(base[k], other[k], rtol=0, atol=1e-9, equal_nan=True), k
 
 
-@pytest.mark.parametrize("variant", [None, "-DOD_EXTRACT_SMEM=1"])
+@pytest.mark.parametrize("variant", [None, "-DOD_EXTRACT_SMEM=1"])       # (OD_INPLACE_Z only touches the contact state machine)
 def test_cooperative_lanes_rocket_and_rollouts_on_the_host(variant):
     """rocket_kernel_g (dense 12×12 dynamics + 10×10 cone projection + chain rule) and the closed-loop rollout template with
     cooperating lanes on emulated warps: identical to their one-lane runs, for the shipped path and the prepared variant."""
@@ -317,11 +324,18 @@ def test_pathological_inputs_agree_across_lanes_and_variants():
     runs = [H.step("hopper", q1, q2, u, 0.05, reg=1), H.step("hopper", q1, q2, u, 0.05, reg=8)]
     with H.use_variant(["-DOD_EXTRACT_SMEM=1"], "_extract"):
         runs += [H.step("hopper", q1, q2, u, 0.05, reg=1), H.step("hopper", q1, q2, u, 0.05, reg=8)]
+    with H.use_variant(["-DOD_EXTRACT_SMEM=1", "-DOD_INPLACE_Z=1"], "_v2z"):
+        runs += [H.step("hopper", q1, q2, u, 0.05, reg=1), H.step("hopper", q1, q2, u, 0.05, reg=8)]
     base = runs[0]
     assert base["st_eval"][1] == 2 and base["st_eval"][5] == 2            # non-finite inputs: ST_FAIL
     assert set(base["st_eval"][[2, 3]]) <= {1, 2}                          # absurd inputs: iteration cap or failure, reported
     assert base["status"][0] == 0 and base["status"][4] == 0
-    for other in runs[1:]:
+    conv = base["status"] == 0
+    for n, other in enumerate(runs[1:]):
         assert np.array_equal(base["status"], other["status"]) and np.array_equal(base["it_eval"], other["it_eval"])
         for k in ("q3", "dq1", "dq2", "du"):
-            assert np.array_equal(base[k], other[k], equal_nan=True), k
+            assert np.array_equal(base[k][conv], other[k][conv], equal_nan=True), k
+            if n < 3:      # shipped path and the mirror variant: bit-identical even on the wandering problems
+                assert np.array_equal(base[k], other[k], equal_nan=True), k
+            else:          # in-place iterate: the retried line-search steps of the two capped problems differ by rounding
+                assert np.allclose(base[k], other[k], rtol=0, atol=1e-6, equal_nan=True), k
