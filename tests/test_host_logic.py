@@ -339,3 +339,56 @@ def test_pathological_inputs_agree_across_lanes_and_variants():
                 assert np.array_equal(base[k], other[k], equal_nan=True), k
             else:          # in-place iterate: the retried line-search steps of the two capped problems differ by rounding
                 assert np.allclose(base[k], other[k], rtol=0, atol=1e-6, equal_nan=True), k
+
+
+def test_user_model_front_end(tmp_path):
+    """a model written as a specification file (tools/codegen/examples/particle_spec.py: point mass, ground
+    contact, Coulomb friction) goes through `gen_models.py --spec` and the generated header + traits struct run under the
+    product's solver templates on the host tier: free flight is the explicit variational step, a particle pressed on the ground
+    stays on it and sticks inside the friction cone / slides outside, and the IFT sensitivities match finite differences."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path)
+    subprocess.check_call([sys.executable, os.path.join(root, "tools", "codegen", "gen_models.py"), "--spec",
+                           os.path.join(root, "tools", "codegen", "examples", "particle_spec.py"), "--out", out],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    hdr = os.path.join(out, "model_particle.cuh")
+    so = os.path.join(out, "libusermodel.so")
+    subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC", "-shared",
+                           "-DUSER_MODEL_HEADER=\"%s\"" % hdr, "-DUSER_MODEL=ParticleModel", "-o", so,
+                           os.path.join(root, "tests", "user_model_check.cu")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    L = C.CDLL(so)
+    dp = C.POINTER(C.c_double)
+
+    def step(q1, q2, u, mu=0.5, h=0.05, reg=0, ke=1e-6, kg=1e-6):
+        q1, q2, u = (np.ascontiguousarray(a, dtype=np.float64).reshape(-1, 2) for a in (q1, q2, u))
+        B = q1.shape[0]
+        q3 = np.zeros((B, 2)); d1 = np.zeros((B, 2, 2)); d2 = np.zeros((B, 2, 2)); du = np.zeros((B, 2, 2)); st = np.zeros(B, dtype=np.int32)
+        fr = np.array([mu, 0, 0, 0.0])
+        p = lambda a: a.ctypes.data_as(dp)
+        assert L.um_step(B, p(q1), p(q2), p(u), C.c_double(h), p(fr), C.c_double(ke), C.c_double(kg), p(q3), p(d1), p(d2), p(du),
+                         st.ctypes.data_as(C.POINTER(C.c_int)), reg) == 0
+        return q3, d1.transpose(0, 2, 1), d2.transpose(0, 2, 1), du.transpose(0, 2, 1), st          # blocks are column-major
+    m, g, h = 1.5, 9.81, 0.05
+    for reg in (0, 1):
+        # free flight: no contact force, q3 = 2 q2 − q1 + h² (u/m − g e_z)
+        q1 = np.array([[0.0, 1.0]]); q2 = np.array([[0.01, 1.02]]); u = np.array([[0.3, 0.2]])
+        q3, d1, d2, du, st = step(q1, q2, u, reg=reg)
+        assert st[0] == 0 and np.allclose(q3[0], 2 * q2[0] - q1[0] + h * h * (u[0] / m - np.array([0.0, g])), atol=1e-6)
+        # resting on the ground, small tangential push inside the friction cone (|u_x| < μ m g): sticks; a large one slides
+        q1 = np.array([[0.0, 0.0]]); q2 = np.array([[0.0, 0.0]])
+        q3, *_ , st = step(q1, q2, np.array([[0.2 * m * g, 0.0]]), reg=reg)
+        assert st[0] == 0 and abs(q3[0, 1]) < 1e-5 and abs(q3[0, 0]) < 1e-5
+        q3, *_ , st = step(q1, q2, np.array([[2.0 * m * g, 0.0]]), reg=reg)
+        assert st[0] == 0 and abs(q3[0, 1]) < 1e-5 and abs(q3[0, 0] - h * h * (2.0 - 0.5) * g) < 1e-5
+        # IFT sensitivities against central differences of the step itself (sliding contact: every block is exercised)
+        q1 = np.array([[0.0, 0.02]]); q2 = np.array([[0.01, 0.005]]); u = np.array([[1.0 * m * g, -2.0]])
+        q3, d1, d2, du, st = step(q1, q2, u, reg=reg, ke=1e-9, kg=1e-9)
+        assert st[0] == 0
+        eps = 1e-6
+        for blk, arr in ((d1, q1), (d2, q2), (du, u)):
+            for j in range(2):
+                ap = arr.copy(); am = arr.copy(); ap[0, j] += eps; am[0, j] -= eps
+                args_p = [ap if a is arr else a for a in (q1, q2, u)]; args_m = [am if a is arr else a for a in (q1, q2, u)]
+                fd = (step(*args_p, reg=reg, ke=1e-9, kg=1e-9)[0][0] - step(*args_m, reg=reg, ke=1e-9, kg=1e-9)[0][0]) / (2 * eps)
+                assert np.allclose(blk[0][:, j], fd, atol=2e-4), (reg, j, blk[0][:, j], fd)

@@ -12,7 +12,10 @@ which generates dense r / rz / rθ, the contact models are emitted in *block* fo
     D = ∂d/∂q   Eγ = ∂d/∂γ   Eb = ∂d/∂b   N = ∂ϕ/∂q   V = ∂vT/∂q   Mψ = ∂ψ̂/∂γ        (jac)
     Dθ = ∂d/∂θ'   Vθ = ∂vT/∂θ'   with θ' = (q1, q2, u) — the columns f/fx/fu return    (jacth)
 
-Run:  python tools/codegen/gen_models.py            (regenerates every header; output is committed)
+Run:  python tools/codegen/gen_models.py            (regenerates every built-in header; output is committed)
+      python tools/codegen/gen_models.py --spec my_model.py --out DIR      (a user-written model specification → DIR/model_<name>.cuh
+                                                                             with the traits struct; format and example:
+                                                                             tools/codegen/examples/particle_spec.py)
 """
 import os
 import sys
@@ -479,7 +482,77 @@ def gen_dense(m):
     return "\n".join(out) + "\n"
 
 
+TRAITS = '''
+// Traits binding od::gen_{name} to the solver templates (csrc/contact_ip.cuh) — same shape as the built-in models of csrc/models.cuh.
+namespace od {{
+struct {cls} {{
+    static constexpr int NQ = gen_{name}::NQ, NU = gen_{name}::NU, NC = gen_{name}::NC, NP = gen_{name}::NP, NB = gen_{name}::NB;
+    static constexpr int NTH = gen_{name}::NTH, NF = {nf}, NTC = gen_{name}::NTC, NTV = gen_{name}::NTV;
+    static constexpr bool ROBUST_IFT = false;          // set to true for models with redundant contact constraints (planar push)
+    __host__ __device__ static constexpr int cone_off(int k) {{ return {off}; }}
+    __host__ __device__ static constexpr int cone_dim(int k) {{ return {dim}; }}
+    OD_HD static void trig_const(const double* th, double* trc) {{ gen_{name}::trig_const(th, trc); }}
+    OD_HD static void trig_var(const double* q, const double* th, double* trv) {{ gen_{name}::trig_var(q, th, trv); }}
+    OD_HD static void eq(const double* q, const double* g, const double* b, const double* th, const double* trc, const double* trv,
+                         double* d, double* phi, double* psit, double* vT) {{ gen_{name}::eq(q, g, b, th, trc, trv, d, phi, psit, vT); }}
+    OD_HD static void jac(const double* q, const double* g, const double* b, const double* th, const double* trc, const double* trv,
+                          double* D, double* Eg, double* Eb, double* N, double* V, double* Mpsi) {{
+        gen_{name}::jac(q, g, b, th, trc, trv, D, Eg, Eb, N, V, Mpsi); }}
+    OD_HD static void jacth(const double* q, const double* g, const double* b, const double* th, const double* trc, const double* trv,
+                            double* Dth, double* Vth) {{ gen_{name}::jacth(q, g, b, th, trc, trv, Dth, Vth); }}
+}};
+}}  // namespace od
+'''
+
+
+def gen_user_model(spec_path, out_dir):
+    """--spec: a user-written model specification (see tools/codegen/examples/particle_spec.py for the format) → one header with
+    the generated device code and the traits struct od::<Name>Model that the solver templates take."""
+    import importlib.util
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("od_user_spec", spec_path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    m = mod.model()
+    need = ["name", "NQ", "NU", "NC", "NP", "NB", "cone_dims", "NTH", "q", "gam", "b", "th", "d", "phi", "psit", "vT"]
+    missing = [k for k in need if k not in m]
+    if missing:
+        raise SystemExit("model(): missing keys %s" % missing)
+    NQ, NU, NC, NP, NB = m["NQ"], m["NU"], m["NC"], m["NP"], m["NB"]
+    if len(m["d"]) != NQ or len(m["phi"]) != NC or len(m["psit"]) != NP or len(m["vT"]) != NB or sum(m["cone_dims"]) != NB or len(m["cone_dims"]) != NP:
+        raise SystemExit("model(): d / phi / psit / vT / cone_dims do not match NQ / NC / NP / NB")
+    nf = m["NTH"] - (2 * NQ + NU) - 1
+    if nf < 0 or len(m["th"]) != m["NTH"]:
+        raise SystemExit("model(): θ must be [q0 (NQ), q1 (NQ), u (NU), friction parameters, h]")
+    m = dict(m)
+    m["q"] = list(m["q"]); m["gam"] = list(m["gam"]) or vec("g", 1); m["b"] = list(m["b"]) or vec("b", 1)
+    offs, o = [], 0
+    for dmn in m["cone_dims"]:
+        offs.append(o); o += dmn
+
+    def chain(vals):                                   # value of entry k as a constexpr expression
+        if not vals:
+            return "0"
+        e = str(vals[-1])
+        for k in range(len(vals) - 2, -1, -1):
+            e = "(k == %d ? %d : %s)" % (k, vals[k], e)
+        return e
+
+    cls = "".join(w.capitalize() for w in m["name"].split("_")) + "Model"
+    src = gen_contact(m) + TRAITS.format(name=m["name"], cls=cls, nf=nf, off=chain(offs), dim=chain(list(m["cone_dims"])))
+    os.makedirs(out_dir, exist_ok=True)
+    path = os.path.join(out_dir, "model_%s.cuh" % m["name"])
+    open(path, "w").write(src)
+    sys.stderr.write("wrote %s (traits struct od::%s)\n" % (path, cls))
+    return path, cls
+
+
 def main():
+    if "--spec" in sys.argv:
+        i = sys.argv.index("--spec")
+        out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else "."
+        gen_user_model(sys.argv[i + 1], out)
+        return
     only = set(sys.argv[1:])
     os.makedirs(OUT, exist_ok=True)
     contact = [("hopper", model_hopper), ("acrobot_impact", lambda: _acrobot(True)), ("acrobot_nominal", lambda: _acrobot(False)),
