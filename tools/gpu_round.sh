@@ -17,3 +17,5 @@ tail -3 gpurun_out/${TAG}_smoke.log; tail -5 gpurun_out/${TAG}_pytest_gpu.log; c
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:contact_step_kernel -s 3 -c 1 -o gpurun_out/${TAG}_prof_iso -f \
     python tools/micro/kernel_time.py hopper 592 5 > gpurun_out/${TAG}_ncu_iso.log 2>&1
 ls -la gpurun_out/ | tail -15
+# fp64 FMA peak of this GPU, for the compute-side reading of the kernel's fp64-pipe utilisation
+[ -x tools/micro/fp64_peak ] && timeout 60 tools/micro/fp64_peak > gpurun_out/${TAG}_fp64_peak.txt 2>&1; tail -1 gpurun_out/${TAG}_fp64_peak.txt
