@@ -50,6 +50,28 @@ def ncu_traffic():
         return None
 
 
+def fp64_side():
+    """Compute-side companion of the (mandated) HBM roofline: measured fp64 FMA peak of the GPU (tools/micro/fp64_peak.cu →
+    profiles/fp64_peak.json) and the fp64-pipe utilisation of the step kernel in the committed ncu capture."""
+    out = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "fp64_peak.json")) as f:
+            out["fp64_fma_peak_tflops"] = float(json.load(f)["fp64_fma_tflops"])
+    except Exception:
+        pass
+    try:
+        with open(os.path.join(ROOT, "profiles", "latest_kernel_summary.json")) as f:
+            l = json.load(f)["launches"][0]
+        for k, v in l.items():
+            if k.startswith("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"):
+                out["fp64_pipe_busy_pct_ncu"] = float(v)
+            if k.startswith("smsp__issue_active.avg.pct_of_peak_sustained_active"):
+                out["issue_slots_busy_pct_ncu"] = float(v)
+    except Exception:
+        pass
+    return out or None
+
+
 class ClockSampler:
     """Samples SM clock and throttle reasons of the local GPU through NVML while the timed region runs."""
 
@@ -364,7 +386,7 @@ def main():
                                       if fused is not None else "kernel + ncclAllGather of 352-B rows"),
                        "gather_check_bitwise_equal_to_nccl": gather_check, "converged_fraction": ok_frac},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
-                         "kernel": "od::contact_step_kernel<HopperModel, lanes=%d, problems/block=%d, register Gauss-Jordan>" % ((8, 4) if B <= 8192 else (4, 8)), "kernel_ms": ker_ms_per, "algorithmic_bytes_per_launch": (BYTES_IN + BYTES_OUT) * B,
+                         "kernel": "od::contact_step_kernel<HopperModel, lanes=%d, problems/block=%d, register Gauss-Jordan>" % ((8, 4) if B <= 8192 else (4, 8)), "kernel_ms": ker_ms_per, "algorithmic_bytes_per_launch": (BYTES_IN + BYTES_OUT) * B, "compute_side": fp64_side(),
                          "peak_source": peak_src,
                          "note": "432 B vs ~1e5 fp64 flop per unit: the kernel is fp64-latency bound by construction (DESIGN.md §Roofline)"},
             "e2e": {"value": B_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": BYTES_IN * B, "d2h_bytes_per_step": (BYTES_OUT + 4) * B,
