@@ -7,8 +7,10 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SO_PATH = os.path.join(_PKG, "liboptdyn_b200.so")
-_SRC = os.path.join(_PKG, "csrc", "optdyn_b200.cu")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+_CSRC = os.path.join(_PKG, "csrc")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
+# kernel switches of the shipped build (A/B variants: build(extra_flags=[...], out=...), tools/gpu_validate_variant.sh)
+DEFAULT_DEFINES = ["-DOD_EXTRACT_SMEM=1"]
 
 _lib = None
 
@@ -23,23 +25,48 @@ class od_options(C.Structure):
 
 def _sources():
     out = []
-    for dp, _, fs in os.walk(os.path.join(_PKG, "csrc")):
+    for dp, _, fs in os.walk(_CSRC):
         out += [os.path.join(dp, f) for f in fs]
     out.append(os.path.join(_ROOT, "include", "optdyn_b200.h"))
     return out
 
 
-def build(force=False, verbose=False):
-    """nvcc -gencode arch=compute_100a,code=sm_100a … → optimization_dynamics_b200/liboptdyn_b200.so (in-tree)."""
-    if not force and os.path.exists(SO_PATH) and os.path.getmtime(SO_PATH) >= max(os.path.getmtime(s) for s in _sources()):
-        return SO_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH, _SRC]
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+def translation_units():
+    """optdyn_b200.cu (C ABI, host side, small kernels) + one unit per contact model (csrc/inst/contact_<model>.cu)."""
+    inst = os.path.join(_CSRC, "inst")
+    return [os.path.join(_CSRC, "optdyn_b200.cu")] + sorted(os.path.join(inst, f) for f in os.listdir(inst) if f.endswith(".cu"))
+
+
+def build(force=False, verbose=False, extra_flags=None, out=None, jobs=None):
+    """nvcc -gencode arch=compute_100a,code=sm_100a … → optimization_dynamics_b200/liboptdyn_b200.so (in-tree).  The translation
+    units are compiled side by side (one nvcc process each) and linked into one shared library."""
+    from concurrent.futures import ThreadPoolExecutor
+    so = out or SO_PATH
+    defines = DEFAULT_DEFINES if extra_flags is None else list(extra_flags)
+    if not force and os.path.exists(so) and os.path.getmtime(so) >= max(os.path.getmtime(s) for s in _sources() + [os.path.abspath(__file__)]):
+        return so
+    objdir = os.path.join(_PKG, "build", os.path.basename(so) + ".o")
+    os.makedirs(objdir, exist_ok=True)
+    units = translation_units()
+    objs = [os.path.join(objdir, os.path.basename(u)[:-3] + ".o") for u in units]
+
+    def compile_one(uo):
+        u, o = uo
+        cmd = ["nvcc"] + NVCC_FLAGS + defines + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", o, u]
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        return u, res.returncode, res.stdout
+
+    with ThreadPoolExecutor(max_workers=jobs or min(len(units), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(compile_one, zip(units, objs)))
+    for u, rc, log in results:
+        if rc != 0:
+            raise RuntimeError("nvcc failed on %s:\n%s" % (u, log))
+        if verbose:
+            print(log)
+    res = subprocess.run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", so] + objs, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout)
-    if verbose:
-        print(res.stdout)
-    return SO_PATH
+        raise RuntimeError("link failed:\n" + res.stdout)
+    return so
 
 
 def lib():

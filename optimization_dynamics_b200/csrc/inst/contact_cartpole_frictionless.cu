@@ -1,0 +1,3 @@
+// Step + rollout kernels of one contact model (see ../launch.cuh): its own translation unit so that the library builds in parallel.
+#include "../launch.cuh"
+namespace od { OD_INSTANTIATE_CONTACT(cartpole_frictionless, CartpoleFrictionlessModel, false, false) }

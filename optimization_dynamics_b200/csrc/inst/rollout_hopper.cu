@@ -1,0 +1,3 @@
+// Rollout kernels of one contact model (see ../launch.cuh): its own translation unit so that the library builds in parallel.
+#include "../launch.cuh"
+namespace od { OD_INSTANTIATE_ROLLOUT(hopper, HopperModel, true, true) }

@@ -1,0 +1,103 @@
+// Launch heuristics + per-model launch entry points of the contact step / rollout kernels.  Every model's kernels are instantiated
+// in ONE translation unit of their own (csrc/inst/contact_<model>.cu) so that liboptdyn_b200.so builds in parallel (the generated
+// model code × lane configurations is what nvcc spends its minutes on); optdyn_b200.cu only sees the declarations below.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdlib.h>
+#include "models.cuh"
+
+namespace od {
+
+template <class M, int G, int PPB, bool REG>
+static inline cudaError_t launch_contact_cfg(const StepArgs& a, cudaStream_t s) {
+    const int grid = (a.B + PPB - 1) / PPB;
+    constexpr size_t smem = sizeof(double) * PPB * ContactIP<M, G, PPB, REG>::WS;
+    if (smem > 48 * 1024) {   // > 48 KB of dynamic shared memory needs an explicit opt-in; per device, so set at every launch
+        cudaError_t e = cudaFuncSetAttribute(contact_step_kernel<M, G, PPB, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    contact_step_kernel<M, G, PPB, REG><<<grid, G * PPB, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+// Lanes per problem: 1 = one thread per problem (throughput configuration, large batches; LU in shared memory); 4 / 8 =
+// cooperative groups (latency configuration: a 4096-problem batch alone would put a single warp on each SM) with the
+// register-resident Gauss–Jordan of group_gj.cuh.  OD_LANES overrides the heuristic; OD_REG=0 forces the shared-memory LU.
+inline int lanes_for(int B, bool heavy = false) {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("OD_LANES"); forced = e ? atoi(e) : 0; }
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16) return forced;
+    // planar push (20×20 reduced system, 35 variables): measured 1024 problems 5.2 / 4.1 / 3.4 ms with 4 / 8 / 16 lanes,
+    // 25 600 problems 12.0 / 10.0 ms with 4 / 8 lanes (register path; shared-memory LU: 5.3 and 12.0 ms)
+    if (heavy) return B <= 4096 ? 16 : 8;
+    if (B <= 2048) return 8;       // measured on B200 (hopper, r02a): 4096 problems 0.0641 ms with 4 lanes, 0.0713 with 8 (solution gathered through the mirror)
+    return 4;                      // 262144 problems: 87 M solves/s with 4 lanes (register path); 1 lane (shared-memory LU) was 57 M against 62 M before
+}
+inline bool reg_path() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("OD_REG"); v = e ? atoi(e) : 1; }
+    return v != 0;
+}
+
+// WIDE: models large enough for 8 lanes; REGOK: models whose IFT runs on the register path (not the rank-revealing one)
+template <class M, bool WIDE, bool REGOK>
+static inline cudaError_t launch_contact(const StepArgs& a, cudaStream_t s) {
+    const int lanes = lanes_for(a.B, M::ROBUST_IFT);
+    if constexpr (REGOK) {
+        if (reg_path()) {
+            if constexpr (WIDE) { if (lanes == 16) return launch_contact_cfg<M, 16, 2, true>(a, s); }
+            if constexpr (WIDE) { if (lanes == 8) return launch_contact_cfg<M, 8, 4, true>(a, s); }
+            if (lanes >= 4) return launch_contact_cfg<M, 4, 8, true>(a, s);
+        }
+    }
+    if constexpr (WIDE) { if (lanes == 8) return launch_contact_cfg<M, 8, 4, false>(a, s); }
+    if (lanes >= 4) return launch_contact_cfg<M, 4, 8, false>(a, s);
+    if constexpr (WIDE) { if (lanes == 2) return launch_contact_cfg<M, 2, 16, false>(a, s); }
+    return launch_contact_cfg<M, 1, 32, false>(a, s);
+}
+
+template <class M, int G, int PPB, bool REG>
+static inline cudaError_t launch_rollout_cfg(const RolloutArgs& a, cudaStream_t s) {
+    const int grid = (a.R + PPB - 1) / PPB;
+    constexpr size_t smem = sizeof(double) * PPB * ContactIP<M, G, PPB, REG>::WS;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(contact_rollout_kernel<M, G, PPB, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    contact_rollout_kernel<M, G, PPB, REG><<<grid, G * PPB, smem, s>>>(a);
+    return cudaGetLastError();
+}
+// rollouts are latency-bound for any realistic count (≤ a few thousand): cooperative lanes, register path where the model has it
+template <class M, bool WIDE, bool REGOK>
+static inline cudaError_t launch_rollout(const RolloutArgs& a, cudaStream_t s) {
+    const int lanes = lanes_for(a.R, M::ROBUST_IFT);
+    if constexpr (REGOK) {
+        if (reg_path()) {
+            if constexpr (WIDE) { if (lanes == 16) return launch_rollout_cfg<M, 16, 2, true>(a, s); }
+            if constexpr (WIDE) { if (lanes == 8) return launch_rollout_cfg<M, 8, 4, true>(a, s); }
+            return launch_rollout_cfg<M, 4, 8, true>(a, s);
+        }
+    }
+    return launch_rollout_cfg<M, 4, 8, false>(a, s);
+}
+
+
+// per-model entry points (defined by OD_INSTANTIATE_CONTACT in csrc/inst/contact_<model>.cu)
+#define OD_DECLARE_CONTACT(NAME)                                                     \
+    cudaError_t od_launch_step_##NAME(const StepArgs& a, cudaStream_t s);            \
+    cudaError_t od_launch_rollout_##NAME(const RolloutArgs& a, cudaStream_t s);
+OD_DECLARE_CONTACT(acrobot_impact)
+OD_DECLARE_CONTACT(acrobot_nominal)
+OD_DECLARE_CONTACT(cartpole_friction)
+OD_DECLARE_CONTACT(cartpole_frictionless)
+OD_DECLARE_CONTACT(planar_push)
+OD_DECLARE_CONTACT(hopper)
+#undef OD_DECLARE_CONTACT
+
+#define OD_INSTANTIATE_STEP(NAME, MODEL, WIDE, REGOK) \
+    cudaError_t od_launch_step_##NAME(const StepArgs& a, cudaStream_t s) { return launch_contact<MODEL, WIDE, REGOK>(a, s); }
+#define OD_INSTANTIATE_ROLLOUT(NAME, MODEL, WIDE, REGOK) \
+    cudaError_t od_launch_rollout_##NAME(const RolloutArgs& a, cudaStream_t s) { return launch_rollout<MODEL, WIDE, REGOK>(a, s); }
+#define OD_INSTANTIATE_CONTACT(NAME, MODEL, WIDE, REGOK) OD_INSTANTIATE_STEP(NAME, MODEL, WIDE, REGOK) OD_INSTANTIATE_ROLLOUT(NAME, MODEL, WIDE, REGOK)
+
+}  // namespace od

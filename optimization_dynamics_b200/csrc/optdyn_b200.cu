@@ -7,7 +7,7 @@
 #include <math.h>
 #include <new>
 #include "../../include/optdyn_b200.h"
-#include "models.cuh"
+#include "launch.cuh"
 #include "dense_ip.cuh"
 #include "rocket.cuh"
 #include "riccati.cuh"
@@ -164,79 +164,8 @@ int64_t od_launch_count(const od_handle* hd) { return hd ? hd->launches : 0; }
 
 }  // extern "C"
 
-template <class M, int G, int PPB, bool REG>
-static cudaError_t launch_contact_cfg(const StepArgs& a, cudaStream_t s) {
-    const int grid = (a.B + PPB - 1) / PPB;
-    constexpr size_t smem = sizeof(double) * PPB * ContactIP<M, G, PPB, REG>::WS;
-    if (smem > 48 * 1024) {   // > 48 KB of dynamic shared memory needs an explicit opt-in; per device, so set at every launch
-        cudaError_t e = cudaFuncSetAttribute(contact_step_kernel<M, G, PPB, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    contact_step_kernel<M, G, PPB, REG><<<grid, G * PPB, smem, s>>>(a);
-    return cudaGetLastError();
-}
-
-// Lanes per problem: 1 = one thread per problem (throughput configuration, large batches; LU in shared memory); 4 / 8 =
-// cooperative groups (latency configuration: a 4096-problem batch alone would put a single warp on each SM) with the
-// register-resident Gauss–Jordan of group_gj.cuh.  OD_LANES overrides the heuristic; OD_REG=0 forces the shared-memory LU.
-static int lanes_for(int B, bool heavy = false) {
-    static int forced = -1;
-    if (forced < 0) { const char* e = getenv("OD_LANES"); forced = e ? atoi(e) : 0; }
-    if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16) return forced;
-    // planar push (20×20 reduced system, 35 variables): measured 1024 problems 5.2 / 4.1 / 3.4 ms with 4 / 8 / 16 lanes,
-    // 25 600 problems 12.0 / 10.0 ms with 4 / 8 lanes (register path; shared-memory LU: 5.3 and 12.0 ms)
-    if (heavy) return B <= 4096 ? 16 : 8;
-    if (B <= 8192) return 8;       // measured on B200 (hopper): 4096 problems 0.0745 ms with 8 lanes, 0.0759 with 4 (earlier kernel: 0.127 with 16, 0.176 with 1)
-    return 4;                      // 262144 problems: 87 M solves/s with 4 lanes (register path); 1 lane (shared-memory LU) was 57 M against 62 M before
-}
-static bool reg_path() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("OD_REG"); v = e ? atoi(e) : 1; }
-    return v != 0;
-}
-
-// WIDE: models large enough for 8 lanes; REGOK: models whose IFT runs on the register path (not the rank-revealing one)
-template <class M, bool WIDE, bool REGOK>
-static cudaError_t launch_contact(const StepArgs& a, cudaStream_t s) {
-    const int lanes = lanes_for(a.B, M::ROBUST_IFT);
-    if constexpr (REGOK) {
-        if (reg_path()) {
-            if constexpr (WIDE) { if (lanes == 16) return launch_contact_cfg<M, 16, 2, true>(a, s); }
-            if constexpr (WIDE) { if (lanes == 8) return launch_contact_cfg<M, 8, 4, true>(a, s); }
-            if (lanes >= 4) return launch_contact_cfg<M, 4, 8, true>(a, s);
-        }
-    }
-    if constexpr (WIDE) { if (lanes == 8) return launch_contact_cfg<M, 8, 4, false>(a, s); }
-    if (lanes >= 4) return launch_contact_cfg<M, 4, 8, false>(a, s);
-    if constexpr (WIDE) { if (lanes == 2) return launch_contact_cfg<M, 2, 16, false>(a, s); }
-    return launch_contact_cfg<M, 1, 32, false>(a, s);
-}
-
-template <class M, int G, int PPB, bool REG>
-static cudaError_t launch_rollout_cfg(const RolloutArgs& a, cudaStream_t s) {
-    const int grid = (a.R + PPB - 1) / PPB;
-    constexpr size_t smem = sizeof(double) * PPB * ContactIP<M, G, PPB, REG>::WS;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(contact_rollout_kernel<M, G, PPB, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    contact_rollout_kernel<M, G, PPB, REG><<<grid, G * PPB, smem, s>>>(a);
-    return cudaGetLastError();
-}
-// rollouts are latency-bound for any realistic count (≤ a few thousand): cooperative lanes, register path where the model has it
-template <class M, bool WIDE, bool REGOK>
-static cudaError_t launch_rollout(const RolloutArgs& a, cudaStream_t s) {
-    const int lanes = lanes_for(a.R, M::ROBUST_IFT);
-    if constexpr (REGOK) {
-        if (reg_path()) {
-            if constexpr (WIDE) { if (lanes == 16) return launch_rollout_cfg<M, 16, 2, true>(a, s); }
-            if constexpr (WIDE) { if (lanes == 8) return launch_rollout_cfg<M, 8, 4, true>(a, s); }
-            return launch_rollout_cfg<M, 4, 8, true>(a, s);
-        }
-    }
-    return launch_rollout_cfg<M, 4, 8, false>(a, s);
-}
-
+// The step / rollout kernels of each contact model are instantiated in their own translation unit (csrc/inst/contact_<model>.cu,
+// through launch.cuh) so that the library builds in parallel; this file holds the host side of the C ABI.
 // Zero-copy output needs whole rows leaving the kernel as contiguous stores (the register path stages the packed row in shared
 // memory); the shared-memory-LU path scatters 8-byte stores, which PCIe handles badly (measured: 2.4x slower end to end).
 static bool rows_leave_coalesced(int model, int B) {
@@ -252,12 +181,12 @@ static int launch_step(od_handle* hd, StepArgs& a) {
     a.opts.ls_scale = hd->opts.ls_scale; a.opts.max_iter = hd->opts.max_iter; a.opts.max_ls = hd->opts.max_ls;
     cudaError_t e;
     switch (hd->model) {
-        case OD_ACROBOT_IMPACT: e = launch_contact<AcrobotImpactModel, false, true>(a, hd->stream); break;
-        case OD_ACROBOT_NOMINAL: e = launch_contact<AcrobotNominalModel, false, false>(a, hd->stream); break;
-        case OD_CARTPOLE_FRICTION: e = launch_contact<CartpoleFrictionModel, false, true>(a, hd->stream); break;
-        case OD_CARTPOLE_FRICTIONLESS: e = launch_contact<CartpoleFrictionlessModel, false, false>(a, hd->stream); break;
-        case OD_PLANAR_PUSH: e = launch_contact<PlanarPushModel, true, true>(a, hd->stream); break;
-        case OD_HOPPER: e = launch_contact<HopperModel, true, true>(a, hd->stream); break;
+        case OD_ACROBOT_IMPACT: e = od_launch_step_acrobot_impact(a, hd->stream); break;
+        case OD_ACROBOT_NOMINAL: e = od_launch_step_acrobot_nominal(a, hd->stream); break;
+        case OD_CARTPOLE_FRICTION: e = od_launch_step_cartpole_friction(a, hd->stream); break;
+        case OD_CARTPOLE_FRICTIONLESS: e = od_launch_step_cartpole_frictionless(a, hd->stream); break;
+        case OD_PLANAR_PUSH: e = od_launch_step_planar_push(a, hd->stream); break;
+        case OD_HOPPER: e = od_launch_step_hopper(a, hd->stream); break;
         default: return fail("this entry point needs a contact model handle (not OD_ROCKET)");
     }
     if (e != cudaSuccess) return fail("contact_step_kernel launch", e);
@@ -441,12 +370,12 @@ int od_rollout_batch_device(od_handle* hd, int R, int T, const double* x1, const
     a.opts.ls_scale = hd->opts.ls_scale; a.opts.max_iter = hd->opts.max_iter; a.opts.max_ls = hd->opts.max_ls;
     cudaError_t e;
     switch (hd->model) {
-        case OD_ACROBOT_IMPACT: e = launch_rollout<AcrobotImpactModel, false, true>(a, hd->stream); break;
-        case OD_ACROBOT_NOMINAL: e = launch_rollout<AcrobotNominalModel, false, false>(a, hd->stream); break;
-        case OD_CARTPOLE_FRICTION: e = launch_rollout<CartpoleFrictionModel, false, true>(a, hd->stream); break;
-        case OD_CARTPOLE_FRICTIONLESS: e = launch_rollout<CartpoleFrictionlessModel, false, false>(a, hd->stream); break;
-        case OD_PLANAR_PUSH: e = launch_rollout<PlanarPushModel, true, true>(a, hd->stream); break;
-        case OD_HOPPER: e = launch_rollout<HopperModel, true, true>(a, hd->stream); break;
+        case OD_ACROBOT_IMPACT: e = od_launch_rollout_acrobot_impact(a, hd->stream); break;
+        case OD_ACROBOT_NOMINAL: e = od_launch_rollout_acrobot_nominal(a, hd->stream); break;
+        case OD_CARTPOLE_FRICTION: e = od_launch_rollout_cartpole_friction(a, hd->stream); break;
+        case OD_CARTPOLE_FRICTIONLESS: e = od_launch_rollout_cartpole_frictionless(a, hd->stream); break;
+        case OD_PLANAR_PUSH: e = od_launch_rollout_planar_push(a, hd->stream); break;
+        case OD_HOPPER: e = od_launch_rollout_hopper(a, hd->stream); break;
         default: return fail("od_rollout_batch: bad model");
     }
     if (e != cudaSuccess) return fail("contact_rollout_kernel launch", e);

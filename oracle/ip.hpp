@@ -40,6 +40,12 @@ struct Options {                         // RoboDojo InteriorPointOptions defaul
     int max_iter = 100, max_ls = 3;
     double eps_min = 0.05, kappa_reg = 1e-3, gamma_reg = 1e-1, undercut = 5.0;
     bool diff_sol = false;
+    // ---- readings of the choices the reference tree does not pin (header above).  Defaults = the oracle's definition of parity;
+    // the alternatives exist so that tests/test_unpinned_choices.py can MEASURE how far q3 and the sensitivities move under each.
+    int tau_rule = 0;          // 0: τ = max(0.95, 1 − vio²);  1: τ = 1 − min(ϵ_min, vio²) (SURVEY A.1 first reading);  2: τ = 0.99 fixed
+    int apply_reg = 0;         // 1: rz += reg·I with reg = κ_vio·γ_reg when κ_vio < κ_reg, and max(reg, κ_tol·γ_reg) in the IFT
+    int mu_mode = 0;           // 0: μ = Σ⟨p,d⟩ / (#orthant pairs + #second-order cones);  1: / total cone dimension
+    int soc_tau_cap = 0;       // 1: second-order-cone step length uses min(τ, 0.99)
     bool diagnostics = false;   // tests only: also report how far the returned iterate is from the exact root (SolveInfo::q_uncertainty)
 };
 
@@ -125,6 +131,7 @@ struct InteriorPoint {
 
     // largest α∈[0,1] with z − αΔ inside the cones, scaled by τ
     double step_length(const double* zz, const double* D, double tau) const {
+        const double tau_soc = opts.soc_tau_cap ? std::min(tau, 0.99) : tau;
         double a = 1.0;
         for (size_t k = 0; k < idx.ort_p.size(); ++k) {
             int ip = idx.ort_p[k], id = idx.ort_d[k];
@@ -132,8 +139,8 @@ struct InteriorPoint {
             if (D[id] > 0.0) a = std::min(a, tau * zz[id] / D[id]);
         }
         for (size_t c = 0; c < idx.soc_p.size(); ++c) {
-            a = std::min(a, soc_step(zz, D, idx.soc_p[c], tau));
-            a = std::min(a, soc_step(zz, D, idx.soc_d[c], tau));
+            a = std::min(a, soc_step(zz, D, idx.soc_p[c], tau_soc));
+            a = std::min(a, soc_step(zz, D, idx.soc_d[c], tau_soc));
         }
         return a;
     }
@@ -173,7 +180,9 @@ struct InteriorPoint {
     SolveInfo solve() {
         SolveInfo info;
         const bool cones = has_cones();
-        const int ncone = (int)idx.ort_p.size() + (int)idx.soc_p.size();
+        int ncone = (int)idx.ort_p.size() + (int)idx.soc_p.size();
+        if (opts.mu_mode == 1) { ncone = (int)idx.ort_p.size(); for (auto& c : idx.soc_p) ncone += (int)c.size(); }
+        double reg = 0.0;
         double daff[NZ], dl[NZ], zc[NZ], rc[NZ];
         eval_r(z, 0.0, r);
         double r_vio = vio(r, idx.equr), k_vio = bil_vio(r);
@@ -186,6 +195,7 @@ struct InteriorPoint {
             }
             info.iterations++;
             eval_rz(z, rz);
+            if (opts.apply_reg) { reg = (k_vio < opts.kappa_reg) ? k_vio * opts.gamma_reg : 0.0; for (int i = 0; i < NZ; ++i) rz[i * NZ + i] += reg; }
             if (!lu_factor(rz, piv, NZ)) { info.status = 2; break; }
             for (int i = 0; i < NZ; ++i) daff[i] = r[i];
             lu_solve(rz, piv, NZ, daff);
@@ -211,7 +221,9 @@ struct InteriorPoint {
             for (int i = 0; i < NZ; ++i) dl[i] = rc[i];
             lu_solve(rz, piv, NZ, dl);
             double viol = std::max(r_vio, k_vio);
-            double tau = std::max(0.95, 1.0 - viol * viol);   // ϵ_min is carried in Options but unused (see header)
+            double tau = std::max(0.95, 1.0 - viol * viol);   // default reading: ϵ_min is carried in Options but unused (see header)
+            if (opts.tau_rule == 1) tau = 1.0 - std::min(opts.eps_min, viol * viol);
+            else if (opts.tau_rule == 2) tau = 0.99;
             double alpha = cones ? step_length(z, dl, tau) : 1.0;
             // residual line search
             double r_c = 0, k_c = 0;
@@ -248,14 +260,15 @@ struct InteriorPoint {
             } else info.q_uncertainty = std::numeric_limits<double>::infinity();
         }
         if (opts.diff_sol && info.status != 2) {
-            if (!differentiate(&info.ift_spread)) info.status = 2;
+            if (!differentiate(&info.ift_spread, opts.apply_reg ? std::max(reg, opts.kappa_tol * opts.gamma_reg) : 0.0)) info.status = 2;
         }
         return info;
     }
 
     // δz = −rz(z*,θ)⁻¹ rθ(z*,θ)
-    bool differentiate(double* spread = nullptr) {
+    bool differentiate(double* spread = nullptr, double reg = 0.0) {
         eval_rz(z, rz);
+        if (reg != 0.0) for (int i = 0; i < NZ; ++i) rz[i * NZ + i] += reg;
         eval_rth(z, rth);
         double alt[NZ * NZ], col[NZ];
         int piv2[NZ];

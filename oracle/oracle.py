@@ -32,6 +32,11 @@ def lib():
     return _LIB
 
 
+def set_variant(tau_rule=0, apply_reg=0, mu_mode=0, soc_tau_cap=0):
+    """Select a reading of the solver choices the reference tree does not pin (oracle/ip.hpp Options).  All zero = default."""
+    lib().od_oracle_set_variant(int(tau_rule), int(apply_reg), int(mu_mode), int(soc_tau_cap))
+
+
 def _p(a, t=C.c_double):
     return None if a is None else a.ctypes.data_as(C.POINTER(t))
 

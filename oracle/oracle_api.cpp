@@ -53,8 +53,12 @@ ConeIndex idx_rocket_proj() {  // rocket/dynamics.jl:52-63 (1-based → 0-based)
     ConeIndex c; c.ort_p = {4, 2}; c.ort_d = {5, 3}; c.soc_p = {{2, 0, 1}}; c.soc_d = {{9, 7, 8}};
     c.equr = range(0, 5); c.ortr = {5, 6}; c.socr = {{7, 8, 9}}; return c; }
 
+// Readings of the unpinned solver choices (ip.hpp Options::tau_rule …): process-wide, set by od_oracle_set_variant.  Tests only.
+int g_variant[4] = {0, 0, 0, 0};
+void apply_variant(Options& o) { o.tau_rule = g_variant[0]; o.apply_reg = g_variant[1]; o.mu_mode = g_variant[2]; o.soc_tau_cap = g_variant[3]; }
+
 Options contact_opts(double r_tol, double kappa_tol, bool diff) {  // src/dynamics.jl:25-33
-    Options o; o.undercut = std::numeric_limits<double>::infinity(); o.gamma_reg = 0.1; o.r_tol = r_tol; o.kappa_tol = kappa_tol;
+    Options o; apply_variant(o); o.undercut = std::numeric_limits<double>::infinity(); o.gamma_reg = 0.1; o.r_tol = r_tol; o.kappa_tol = kappa_tol;
     o.max_ls = 25; o.eps_min = 0.25; o.diff_sol = diff; return o; }
 
 struct StepOut { double* q3; double* dq1; double* dq2; double* du; double* dz_full; SolveInfo info; };
@@ -134,6 +138,7 @@ SolveInfo rocket_projection(const double* u, double u_max, bool diff, double* up
     static const ConeIndex ci = idx_rocket_proj();
     Options o; o.r_tol = 1e-8; o.kappa_tol = 1e-4; o.max_ls = 25; o.eps_min = 0.0; o.undercut = std::numeric_limits<double>::infinity();
     o.gamma_reg = 0.0; o.kappa_reg = 0.0; o.diff_sol = diff;   // rocket/dynamics.jl:77-86
+    apply_variant(o);
     RocketProjection m;
     InteriorPoint<RocketProjection, 10, 4> ip(m, ci, o);
     ip.n_out_rows = 3;
@@ -209,6 +214,11 @@ int least_squares_fit(int N, int ny, int nz, const double* fz, const double* fet
 }  // namespace
 
 extern "C" {
+
+// tau_rule, apply_reg, mu_mode, soc_tau_cap — see ip.hpp Options.  All zero = the oracle's definition of parity.
+void od_oracle_set_variant(int tau_rule, int apply_reg, int mu_mode, int soc_tau_cap) {
+    g_variant[0] = tau_rule; g_variant[1] = apply_reg; g_variant[2] = mu_mode; g_variant[3] = soc_tau_cap;
+}
 
 int od_oracle_dims(int model, int* nq, int* nu, int* nz, int* nth) {
     Dims d; if (!dims_of(model, &d)) return 1; *nq = d.nq; *nu = d.nu; *nz = d.nz; *nth = d.nth; return 0;

@@ -8,7 +8,8 @@ MODE=${1:?build|run}; TAG=${2:?tag}; shift 2
 SO=tools/micro/_ab/${TAG}.so
 if [ "$MODE" = build ]; then
   mkdir -p tools/micro/_ab
-  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared "$@" -o $SO optimization_dynamics_b200/csrc/optdyn_b200.cu && ls -la $SO
+  # all flags of the variant must be given (they REPLACE _lib.DEFAULT_DEFINES)
+  python -c "import sys; from optimization_dynamics_b200 import _lib; print(_lib.build(force=True, extra_flags=sys.argv[2:], out=sys.argv[1]))" $PWD/$SO "$@" && ls -la $SO
   exit $?
 fi
 mkdir -p gpurun_out
