@@ -72,6 +72,14 @@ int od_step_batch(od_handle* hd, int B, const double* q1, const double* q2, cons
  * q3 may be NULL (fx/fu only). */
 int od_step_grad_batch(od_handle* hd, int B, const double* q1, const double* q2, const double* u,
                        double* q3, double* dq3dq1, double* dq3dq2, double* dq3du1, int32_t* status);
+/* RoboDojo.step!(sim, q, v, u, t) for a batch — the call shape the reference's hopper example uses directly
+ * (reference examples/hopper.jl:63,89,112,133,157; inside f / fx / fu at src/dynamics.jl:88,103,123): q: B×nq current
+ * configuration, v: B×nq velocity (the data vector takes q1 = q − h·v), u: B×nu.
+ * grad_sim = 0: the eval simulator (κ_eval_tol, diff_sol = false) → q3.
+ * grad_sim = 1: the gradient simulator (κ_grad_tol, diff_sol = true) → q3 (may be NULL) at κ_grad_tol and
+ *               grad.∂q3∂q1[1], ∂q3∂q2[1], ∂q3∂u1[1] (column-major blocks, all three required).  Host pointers. */
+int od_sim_step_batch(od_handle* hd, int B, int grad_sim, const double* q, const double* v, const double* u,
+                      double* q3, double* dq3dq1, double* dq3dq2, double* dq3du1, int32_t* status);
 /* Same, one packed host row per problem in and out (fewest transfers: 1 H2D, 2 D2H). */
 int od_step_grad_packed(od_handle* hd, int B, const double* in, double* out, int32_t* status);
 

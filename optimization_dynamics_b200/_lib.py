@@ -90,6 +90,7 @@ def lib():
         "od_step_batch": (i, [vp, i, dp, dp, dp, dp, ip]),
         "od_step_grad_batch": (i, [vp, i, dp, dp, dp, dp, dp, dp, dp, ip]),
         "od_step_grad_packed": (i, [vp, i, dp, dp, ip]),
+        "od_sim_step_batch": (i, [vp, i, i, dp, dp, dp, dp, dp, dp, dp, ip]),
         "od_step_grad_batch_device": (i, [vp, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i]),
         "od_step_grad_packed_device": (i, [vp, i, vp, vp, vp, vp, i, i]),
         "od_step_grad_packed_gather_device": (i, [vp, i, vp, C.c_longlong, i, i, C.POINTER(C.c_uint64), vp, vp]),
@@ -115,7 +116,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = ["od_default_options", "od_model_dims", "od_create", "od_destroy", "od_set_stream", "od_synchronize", "od_step_batch",
-                    "od_step_grad_batch", "od_step_grad_packed", "od_step_grad_batch_device", "od_step_grad_packed_device", "od_step_grad_packed_gather_device", "od_step_grad_packed_gather_sync_device", "od_bundle_batch",
+                    "od_step_grad_batch", "od_step_grad_packed", "od_sim_step_batch", "od_step_grad_batch_device", "od_step_grad_packed_device", "od_step_grad_packed_gather_device", "od_step_grad_packed_gather_sync_device", "od_bundle_batch",
                     "od_rollout_batch", "od_rollout_batch_device", "od_riccati_batch", "od_riccati_batch_device",
                     "od_rocket_batch", "od_rocket_batch_device", "od_rocket_projection_batch", "od_launch_count", "od_last_error", "od_version"]
 

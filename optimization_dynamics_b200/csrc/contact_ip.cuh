@@ -853,6 +853,9 @@ struct StepArgs {
     int packed_out;
     // Packed input (q2 = q1 + NQ, u = q1 + 2NQ, one stride): the register path loads the row cooperatively.
     int in_packed;
+    // RoboDojo.step!(sim, q, v, u, t) call shape (reference examples/hopper.jl:63,89,112,133,157): the `q1` array holds the velocity
+    // v1 and the data vector takes q1 = q2 − h·v1 directly (no (q2 − q1)/h round trip).
+    int in_vel;
     // Cross-GPU barrier fused into the kernel (replaces the separate barrier launch after the fused all-gather): every thread
     // fences its peer stores, the last block of the grid to finish publishes `sync_epoch` into slot `self_rank` of every peer's
     // flag array and waits until every peer has published it here.  sync_flags[r] = rank r's flag array (world × u64) as mapped
@@ -923,7 +926,7 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
         for (int k = 0; k < NQ; ++k) {
             double x1 = xin[k], x2 = xin[NQ + k];
             if (pe) { x1 += pe[k]; x2 += pe[NQ + k]; }
-            const double v1 = (x2 - x1) / a.h;                 // src/dynamics.jl:84-86
+            const double v1 = a.in_vel ? x1 : (x2 - x1) / a.h; // src/dynamics.jl:84-86 (or the caller's v1: step!(sim, q2, v1, u1, t))
             th[k] = x2 - a.h * v1;                             // RoboDojo.step!: q1 = q2 − h v1
             th[NQ + k] = x2;
             q2v[k] = x2;
@@ -1112,8 +1115,13 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
 }
 
 // BLOCK = G·PPB threads; dynamic shared memory = PPB × ContactIP::WS doubles.
+// OD_MIN_BLOCKS (A/B switch): minimum resident blocks per SM asked of ptxas — caps the registers per thread (16 → 128) to trade
+// spills for occupancy at saturating batches.
+#ifndef OD_MIN_BLOCKS
+#define OD_MIN_BLOCKS 1
+#endif
 template <class M, int G, int PPB, bool REG>
-__global__ void __launch_bounds__(G * PPB) contact_step_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(G * PPB, OD_MIN_BLOCKS) contact_step_kernel(const StepArgs a) {
     extern __shared__ __align__(16) double od_smem[];
     const int slot = threadIdx.x / G, g = threadIdx.x % G;
     static_assert((G * PPB) % 32 == 0, "whole warps: the step runs warp-synchronously");
@@ -1180,7 +1188,7 @@ OD_HD void contact_rollout_one(const RolloutArgs& ra, const int r, double* ws, c
     for (int k = 0; k < 4; ++k) a.fric[k] = ra.fric[k];
     a.want_eval = 1; a.want_grad = 0; a.eta = nullptr; a.n_eta = 0;
     a.n_peers = 0; a.self_rank = 0; a.gather_row0 = 0; a.gather_width = 0;
-    a.packed_out = 0; a.in_packed = 0; a.sync_counter = nullptr; a.sync_epoch = 0;
+    a.packed_out = 0; a.in_packed = 0; a.in_vel = 0; a.sync_counter = nullptr; a.sync_epoch = 0;
     a.opts = ra.opts;
     const double alpha = ra.alpha ? ra.alpha[r] : 1.0;
     const double* ub = ra.ubar + (size_t)r * ra.ubar_stride;

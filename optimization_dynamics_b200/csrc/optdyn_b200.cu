@@ -71,6 +71,20 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+struct PinBuf {               // page-locked, device-mapped host staging (cudaHostAlloc)
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocMapped);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 struct od_handle {
     int model, device;
     double h;
@@ -78,6 +92,7 @@ struct od_handle {
     double params[4];
     cudaStream_t stream; bool own_stream;
     DevBuf in, out, st, aux, aux2;
+    PinBuf hin, hout;
     int64_t launches;
 };
 
@@ -143,6 +158,7 @@ void od_destroy(od_handle* hd) {
     cudaSetDevice(hd->device);
     cudaStreamSynchronize(hd->stream);
     hd->in.release(); hd->out.release(); hd->st.release(); hd->aux.release(); hd->aux2.release();
+    hd->hin.release(); hd->hout.release();
     if (hd->own_stream) cudaStreamDestroy(hd->stream);
     delete hd;
 }
@@ -173,12 +189,15 @@ static bool rows_leave_coalesced(int model, int B) {
     return regok && reg_path() && lanes_for(B) >= 4;
 }
 
-static int launch_step(od_handle* hd, StepArgs& a) {
+// grad_sim_q3: the eval tolerance is replaced by the gradient tolerance, so that q3 is the gradient simulator's own result
+// (step!(grad_sim, …) of the reference returns q3 at κ_grad_tol)
+static int launch_step(od_handle* hd, StepArgs& a, bool grad_sim_q3 = false) {
     if (a.B <= 0) return 0;
     a.h = hd->h;
     for (int k = 0; k < 4; ++k) a.fric[k] = hd->params[k];
     a.opts.r_tol = hd->opts.r_tol; a.opts.kappa_eval_tol = hd->opts.kappa_eval_tol; a.opts.kappa_grad_tol = hd->opts.kappa_grad_tol;
     a.opts.ls_scale = hd->opts.ls_scale; a.opts.max_iter = hd->opts.max_iter; a.opts.max_ls = hd->opts.max_ls;
+    if (grad_sim_q3) a.opts.kappa_eval_tol = hd->opts.kappa_grad_tol;
     cudaError_t e;
     switch (hd->model) {
         case OD_ACROBOT_IMPACT: e = od_launch_step_acrobot_impact(a, hd->stream); break;
@@ -317,36 +336,89 @@ int od_step_grad_packed(od_handle* hd, int B, const double* in, double* out, int
     return 0;
 }
 
+// Separate host arrays → ONE packed, pinned staging row per problem → one H2D copy, one launch; the kernel writes the finished
+// packed rows (and, behind them, the status words) straight into the pinned output staging (or, for the models whose rows do not
+// leave coalesced, one D2H copy brings rows + status back) → unpack on the host.  Replaces 3 H2D + 5 D2H copies per call; for a
+// single problem (the reference's per-timestep f / fx / fu call shape) the call is launch + synchronise.
+//   in_vel: the first array is v1, not q1 (RoboDojo.step! call shape);  sim: -1 = f + fx/fu in one pass (q3 at κ_eval_tol, IFT at
+//   κ_grad_tol), 0 = eval simulator only, 1 = gradient simulator only (q3 AND the IFT at κ_grad_tol, like step!(grad_sim, …)).
+static int step_host_rows(od_handle* hd, int B, const double* a0, const double* q2, const double* u, int in_vel, int sim,
+                          double* q3, double* dq1, double* dq2, double* du, int32_t* status) {
+    Dims d; dims_of(hd->model, &d);
+    const size_t nq = d.nq, nu = d.nu, inw = 2 * nq + nu;
+    const bool want_grad = sim != 0 && dq1;
+    const size_t outw = want_grad ? nq + nq * inw : nq;          // eval only: compact q3 rows
+    OD_CUDA(cudaSetDevice(hd->device));
+    const size_t in_bytes = sizeof(double) * inw * B, out_bytes = sizeof(double) * outw * B, st_bytes = sizeof(int32_t) * B;
+    OD_CUDA(hd->hin.reserve(in_bytes));
+    OD_CUDA(hd->hout.reserve(out_bytes + st_bytes));
+    OD_CUDA(hd->in.reserve(in_bytes));
+    double* hin = (double*)hd->hin.p; double* hout = (double*)hd->hout.p; int32_t* hst = (int32_t*)((char*)hd->hout.p + out_bytes);
+    for (int i = 0; i < B; ++i) {
+        double* r = hin + (size_t)i * inw;
+        memcpy(r, a0 + (size_t)i * nq, sizeof(double) * nq);
+        memcpy(r + nq, q2 + (size_t)i * nq, sizeof(double) * nq);
+        memcpy(r + 2 * nq, u + (size_t)i * nu, sizeof(double) * nu);
+    }
+    OD_CUDA(cudaMemcpyAsync(hd->in.p, hin, in_bytes, cudaMemcpyHostToDevice, hd->stream));
+    const bool zc = want_grad && rows_leave_coalesced(hd->model, B) && zero_copy_mode() >= 1;
+    double* dout = nullptr; int32_t* dst = nullptr;
+    if (zc) {
+        OD_CUDA(cudaHostGetDevicePointer((void**)&dout, hout, 0));
+        dst = (int32_t*)((char*)dout + out_bytes);
+    } else {
+        OD_CUDA(hd->out.reserve(out_bytes + st_bytes));
+        dout = (double*)hd->out.p; dst = (int32_t*)((char*)hd->out.p + out_bytes);
+    }
+    const double* din = (const double*)hd->in.p;
+    StepArgs a; memset(&a, 0, sizeof(a));
+    a.B = B; a.q1 = din; a.q2 = din + nq; a.u = din + 2 * nq; a.in_stride_q = (int)inw; a.in_stride_u = (int)inw; a.in_packed = 1; a.in_vel = in_vel;
+    a.q3 = dout; a.dq1 = want_grad ? dout + nq : nullptr; a.dq2 = dout + nq + nq * nq; a.du = dout + nq + 2 * nq * nq;
+    a.out_stride_q3 = (int)outw; a.out_stride_dq = (int)outw; a.out_stride_du = (int)outw;
+    a.status = dst; a.want_eval = (sim != 1 || q3) ? 1 : 0; a.want_grad = want_grad ? 1 : 0;
+    a.packed_out = ((reinterpret_cast<uintptr_t>(dout) & 15) == 0) ? 1 : 0;
+    if (launch_step(hd, a, sim == 1)) return 1;
+    if (!zc) OD_CUDA(cudaMemcpyAsync(hout, dout, out_bytes + st_bytes, cudaMemcpyDeviceToHost, hd->stream));
+    OD_CUDA(cudaStreamSynchronize(hd->stream));
+    for (int i = 0; i < B; ++i) {
+        const double* r = hout + (size_t)i * outw;
+        if (q3) memcpy(q3 + (size_t)i * nq, r, sizeof(double) * nq);
+        if (want_grad) {
+            memcpy(dq1 + (size_t)i * nq * nq, r + nq, sizeof(double) * nq * nq);
+            memcpy(dq2 + (size_t)i * nq * nq, r + nq + nq * nq, sizeof(double) * nq * nq);
+            memcpy(du + (size_t)i * nq * nu, r + nq + 2 * nq * nq, sizeof(double) * nq * nu);
+        }
+    }
+    if (status) memcpy(status, hst, st_bytes);
+    return 0;
+}
+
 int od_step_grad_batch(od_handle* hd, int B, const double* q1, const double* q2, const double* u,
                        double* q3, double* dq1, double* dq2, double* du, int32_t* status) {
     if (!hd) return fail("null handle");
-    Dims d; dims_of(hd->model, &d);
     if (hd->model == OD_ROCKET) return fail("od_step_grad_batch: use od_rocket_batch for OD_ROCKET");
     if (B <= 0) return 0;
+    if (!q1 || !q2 || !u) return fail("od_step_grad_batch: null input");
     const bool want_grad = dq1 || dq2 || du;
     if (want_grad && !(dq1 && dq2 && du)) return fail("od_step_grad_batch: gradient outputs must be all null or all non-null");
     if (!want_grad && !q3) return fail("od_step_grad_batch: nothing to compute");
-    OD_CUDA(cudaSetDevice(hd->device));
-    const size_t nq = d.nq, nu = d.nu, inw = 2 * nq + nu, outw = nq + nq * inw;
-    OD_CUDA(hd->in.reserve(sizeof(double) * inw * B));
-    OD_CUDA(hd->out.reserve(sizeof(double) * outw * B));
-    OD_CUDA(hd->st.reserve(sizeof(int32_t) * B));
-    double* din = (double*)hd->in.p; double* dout = (double*)hd->out.p;
-    double *d_q1 = din, *d_q2 = din + nq * B, *d_u = din + 2 * nq * B;
-    double *d_q3 = dout, *d_dq1 = dout + nq * B, *d_dq2 = d_dq1 + nq * nq * B, *d_du = d_dq2 + nq * nq * B;
-    OD_CUDA(cudaMemcpyAsync(d_q1, q1, sizeof(double) * nq * B, cudaMemcpyHostToDevice, hd->stream));
-    OD_CUDA(cudaMemcpyAsync(d_q2, q2, sizeof(double) * nq * B, cudaMemcpyHostToDevice, hd->stream));
-    OD_CUDA(cudaMemcpyAsync(d_u, u, sizeof(double) * nu * B, cudaMemcpyHostToDevice, hd->stream));
-    if (od_step_grad_batch_device(hd, B, d_q1, d_q2, d_u, q3 ? d_q3 : nullptr, d_dq1, d_dq2, d_du, (int32_t*)hd->st.p, nullptr, q3 != nullptr, want_grad)) return 1;
-    if (q3) OD_CUDA(cudaMemcpyAsync(q3, d_q3, sizeof(double) * nq * B, cudaMemcpyDeviceToHost, hd->stream));
-    if (want_grad) {
-        OD_CUDA(cudaMemcpyAsync(dq1, d_dq1, sizeof(double) * nq * nq * B, cudaMemcpyDeviceToHost, hd->stream));
-        OD_CUDA(cudaMemcpyAsync(dq2, d_dq2, sizeof(double) * nq * nq * B, cudaMemcpyDeviceToHost, hd->stream));
-        OD_CUDA(cudaMemcpyAsync(du, d_du, sizeof(double) * nq * nu * B, cudaMemcpyDeviceToHost, hd->stream));
+    return step_host_rows(hd, B, q1, q2, u, 0, want_grad ? (q3 ? -1 : 1) : 0, q3, dq1, dq2, du, status);
+}
+
+// RoboDojo.step!(sim, q, v, u, t) for a batch — the call the reference's hopper example makes directly
+// (reference examples/hopper.jl:63,89,112,133,157; inside f / fx / fu at src/dynamics.jl:88,103,123).
+int od_sim_step_batch(od_handle* hd, int B, int grad_sim, const double* q, const double* v, const double* u,
+                      double* q3, double* dq3dq1, double* dq3dq2, double* dq3du1, int32_t* status) {
+    if (!hd) return fail("null handle");
+    if (hd->model == OD_ROCKET) return fail("od_sim_step_batch: contact models only");
+    if (B <= 0) return 0;
+    if (!q || !v || !u) return fail("od_sim_step_batch: null input");
+    if (grad_sim) {
+        if (!(dq3dq1 && dq3dq2 && dq3du1)) return fail("od_sim_step_batch: the gradient simulator needs all three Jacobian outputs");
+        return step_host_rows(hd, B, v, q, u, 1, 1, q3, dq3dq1, dq3dq2, dq3du1, status);
     }
-    if (status) OD_CUDA(cudaMemcpyAsync(status, hd->st.p, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, hd->stream));
-    OD_CUDA(cudaStreamSynchronize(hd->stream));
-    return 0;
+    if (!q3) return fail("od_sim_step_batch: q3 is null");
+    return step_host_rows(hd, B, v, q, u, 1, 0, q3, nullptr, nullptr, nullptr, status);
 }
 
 int od_step_batch(od_handle* hd, int B, const double* q1, const double* q2, const double* u, double* q3, int32_t* status) {

@@ -58,6 +58,72 @@ def _f64(a, shape):
     return a.reshape(shape)
 
 
+class SimulatorGrad:
+    """`sim.grad` of a RoboDojo Simulator as the reference reads it (examples/hopper.jl:97-99,141-142,159; sized at
+    src/dynamics.jl:39-46): 1-element lists (T = 1) of the column-major-in-Julia blocks, here [nq, ncol] arrays.
+    Python identifiers cannot contain `∂`, so the fields are spelled dq3dq1 / dq3dq2 / dq3du1; the reference's names work through
+    getattr(sim.grad, "∂q3∂q1")."""
+    _ALIASES = {"∂q3∂q1": "dq3dq1", "∂q3∂q2": "dq3dq2", "∂q3∂u1": "dq3du1"}
+
+    def __init__(self, nq, nu):
+        self.dq3dq1 = [np.zeros((nq, nq))]
+        self.dq3dq2 = [np.zeros((nq, nq))]
+        self.dq3du1 = [np.zeros((nq, nu))]
+
+    def __getattr__(self, name):
+        alias = SimulatorGrad._ALIASES.get(name)
+        if alias is None:
+            raise AttributeError(name)
+        return getattr(self, alias)
+
+
+class Simulator:
+    """What `model.eval_sim` / `model.grad_sim` are to the reference's callers (src/dynamics.jl:1-14,16-49): `.h`, `.model`
+    (`.model.nq` …), `.grad.∂q3∂{q1,q2,u1}[1]`, and the target of `RoboDojo.step!(sim, q2, v1, u1, t)` (`robodojo.step`).  A proxy:
+    both simulators of one ImplicitDynamics share its device handle; `diff_sol` selects κ_tol and whether the IFT runs."""
+
+    def __init__(self, owner, diff_sol):
+        self._owner = owner
+        self.diff_sol = bool(diff_sol)
+        self.model = owner.model
+        self.h = owner.h
+        self.grad = SimulatorGrad(owner.nq, owner.nu)
+        self.status = 0
+
+    @property
+    def κ_tol(self):
+        return self._owner.opts.kappa_grad_tol if self.diff_sol else self._owner.opts.kappa_eval_tol
+
+    def step(self, q, v, u, t=1):
+        """q3 = step!(sim, q, v, u, t) for one problem; the gradient simulator also refreshes `sim.grad`."""
+        o = self._owner
+        q = _f64(q, (1, o.nq)); v = _f64(v, (1, o.nq)); u = _f64(np.asarray(u, dtype=np.float64)[o.idx_u1] if np.size(u) != o.nu else u, (1, o.nu))
+        q3 = np.empty((1, o.nq)); st = np.empty(1, dtype=np.int32)
+        L = _lib.lib()
+        if self.diff_sol:
+            d1 = np.empty((1, o.nq, o.nq)); d2 = np.empty((1, o.nq, o.nq)); du = np.empty((1, o.nu, o.nq))
+            _lib.check(L.od_sim_step_batch(o._handle(), 1, 1, _dp(q), _dp(v), _dp(u), _dp(q3), _dp(d1), _dp(d2), _dp(du), _ip(st)))
+            self.grad.dq3dq1[0] = d1[0].T; self.grad.dq3dq2[0] = d2[0].T; self.grad.dq3du1[0] = du[0].T
+        else:
+            _lib.check(L.od_sim_step_batch(o._handle(), 1, 0, _dp(q), _dp(v), _dp(u), _dp(q3), None, None, None, _ip(st)))
+        self.status = int(st[0])
+        return q3[0]
+
+    def step_batch(self, q, v, u):
+        """Batched step!: returns (q3[B,nq], status[B]) and, for the gradient simulator, also the three Jacobian stacks [B,nq,ncol]."""
+        o = self._owner
+        q = _f64(q, (-1, o.nq)); B = q.shape[0]
+        v = _f64(v, (B, o.nq)); u = _f64(u, (B, o.nu))
+        q3 = np.empty((B, o.nq)); st = np.empty(B, dtype=np.int32)
+        L = _lib.lib()
+        if not self.diff_sol:
+            _lib.check(L.od_sim_step_batch(o._handle(), B, 0, _dp(q), _dp(v), _dp(u), _dp(q3), None, None, None, _ip(st)))
+            return q3, st
+        d1 = np.empty((B, o.nq, o.nq)); d2 = np.empty((B, o.nq, o.nq)); du = np.empty((B, o.nu, o.nq))
+        _lib.check(L.od_sim_step_batch(o._handle(), B, 1, _dp(q), _dp(v), _dp(u), _dp(q3), _dp(d1), _dp(d2), _dp(du), _ip(st)))
+        return q3, d1.transpose(0, 2, 1), d2.transpose(0, 2, 1), du.transpose(0, 2, 1), st
+
+
 class ImplicitDynamics:
     def __init__(self, model, h, r_func=None, rz_func=None, rθ_func=None, T=1, r_tol=1.0e-8, κ_eval_tol=1.0e-6, κ_grad_tol=1.0e-6,
                  no_impact=False, no_friction=False, n=None, m=None, d=None, nc=None, nb=None, info=None, device=0,
@@ -87,6 +153,10 @@ class ImplicitDynamics:
         self._lib = L
         self._memo_key = None      # (x, u) of the last gradient solve: fx and fu share one launch (reference solves twice)
         self._memo = None
+        # the two simulators of the reference struct (src/dynamics.jl:2-3,60-64): eval_sim (diff_sol = false, κ_eval_tol) and
+        # grad_sim (diff_sol = true, κ_grad_tol) — what examples/hopper.jl:52-160 drives through RoboDojo.step!
+        self.eval_sim = Simulator(self, False)
+        self.grad_sim = Simulator(self, True)
 
     # the reference mutates model.friction after construction (examples/cartpole.jl:21); re-create the handle if it changed
     def _make_handle(self):
@@ -167,6 +237,7 @@ class ImplicitDynamics:
     # ---- single-problem gradient with memoisation --------------------------------------------------------------------------
     def _grad(self, x, u):
         x = np.asarray(x, dtype=np.float64); u = np.asarray(u, dtype=np.float64)
+        self._handle()             # a mutated model.friction (examples/cartpole.jl:21) re-creates the handle and drops the memo
         key = (x.tobytes(), u.tobytes())
         if key != self._memo_key:
             q1 = x[self.idx_q1]; q2 = x[self.idx_q2]

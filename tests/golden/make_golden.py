@@ -18,8 +18,11 @@ from optimization_dynamics_b200 import workloads as W   # noqa: E402
 from common import CONFIGS              # noqa: E402
 
 B = 96
+REF_IN = os.path.join(HERE, "reference_inputs")       # the same inputs as text, for julia/dump_reference_golden.jl (17 significant digits: exact)
+os.makedirs(REF_IN, exist_ok=True)
 for name, (gen, h, ke, kg, fric, _) in CONFIGS.items():
     q1, q2, u = gen(B, h=h, seed=2024)
+    np.savetxt(os.path.join(REF_IN, name + ".csv"), np.concatenate([q1, q2, u], axis=1), delimiter=",", fmt="%.17g")
     e = O.step_batch(name, q1, q2, u, h, ke, False, fric=fric)
     g = O.step_batch(name, q1, q2, u, h, kg, True, fric=fric)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), q1=q1, q2=q2, u=u, q3=e["q3"], dq1=g["dq1"], dq2=g["dq2"], du=g["du"],
@@ -27,6 +30,7 @@ for name, (gen, h, ke, kg, fric, _) in CONFIGS.items():
                         margin=np.minimum(e["margin"], g["margin"]), ift_spread=g["ift_spread"],
                         q_uncertainty=np.maximum(e["q_uncertainty"], g["q_uncertainty"]))
 x, u = W.rocket_batch(B, seed=2024)
+np.savetxt(os.path.join(REF_IN, "rocket.csv"), np.concatenate([x, u], axis=1), delimiter=",", fmt="%.17g")
 for proj, name in ((False, "rocket"), (True, "rocket_proj")):
     r = O.rocket_batch(x, u, 0.05, 12.5, proj, True)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), x=x, u=u, y=r["y"], dx=r["dx"], du=r["du"], uproj=r["uproj"], status=r["status"],

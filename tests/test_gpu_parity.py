@@ -265,3 +265,121 @@ def test_riccati_backward_pass_and_full_ilqr_iteration(od, O):
     Xo, Uo, so = O.rollout_batch("hopper", np.tile(X[0, 0], (8, 1)), U[0], h, 1e-4, xbar=X[0], K=K[0], k=k[0], alpha=al)
     ok = (sn == 0).all(axis=1) & (so == 0).all(axis=1)
     assert ok.sum() >= 6 and np.abs(Xn - Xo)[ok].max() < 1e-6
+
+
+def test_hopper_example_call_surface(od, O):
+    """The north-star example does NOT go through f / fx / fu: reference examples/hopper.jl:52-160 defines f1 / f1u / ft / ftx / ftu
+    on top of model.eval_sim / model.grad_sim, RoboDojo.step!(sim, q2, v1, u1, 1) and model.grad_sim.grad.∂q3∂{q1,q2,u1}[1].
+    Below is a line-by-line transliteration of those five functions on the proxies (Julia 1-based ranges → numpy index arrays;
+    `∂` is not a legal Python identifier character, hence getattr) checked against the oracle."""
+    RoboDojo = od.robodojo
+    hopper = RoboDojo.hopper
+    h = 0.05
+    nq, nu = hopper.nq, hopper.nu
+
+    class ParameterOptInfo:                                            # examples/hopper.jl:16-36
+        def __init__(self):
+            self.idx_q1 = np.arange(nq); self.idx_q2 = nq + np.arange(nq); self.idx_u1 = np.arange(nu)
+            self.idx_uθ = nu + np.arange(2 * nq); self.idx_uθ1 = nu + np.arange(nq); self.idx_uθ2 = nu + nq + np.arange(nq)
+            self.idx_xθ = 2 * nq + np.arange(2 * nq); self.v1 = np.zeros(nq)
+    info = ParameterOptInfo()
+    mk = lambda n, m: od.ImplicitDynamics(hopper, h, RoboDojo.residual_expr(hopper), RoboDojo.jacobian_var_expr(hopper),     # noqa: E731
+                                          RoboDojo.jacobian_data_expr(hopper), r_tol=1.0e-8, κ_eval_tol=1.0e-4, κ_grad_tol=1.0e-3,
+                                          n=n, m=m, nc=4, nb=2, info=info)
+    im_dyn1 = mk(2 * nq, nu + 2 * nq)                                  # examples/hopper.jl:38-43
+    im_dynt = mk(4 * nq, nu)                                           # :45-50
+    G = lambda model, name: getattr(model.grad_sim.grad, name)[0]     # model.grad_sim.grad.∂q3∂q1[1]   # noqa: E731
+
+    def f1(d, model, x, u, w):                                         # :52-70
+        θ = u[model.info.idx_uθ]; q1 = u[model.info.idx_uθ1]; q2 = u[model.info.idx_uθ2]; u1 = u[model.info.idx_u1]
+        model.info.v1[:] = q2; model.info.v1 -= q1; model.info.v1 /= model.eval_sim.h
+        q3 = RoboDojo.step(model.eval_sim, q2, model.info.v1, u1, 1)
+        d[model.info.idx_q1] = q2; d[model.info.idx_q2] = q3; d[model.info.idx_xθ] = θ
+        return d
+
+    def f1u(du, model, x, u, w):                                       # :77-102
+        nq = model.grad_sim.model.nq
+        q1 = u[model.info.idx_uθ1]; q2 = u[model.info.idx_uθ2]; u1 = u[model.info.idx_u1]
+        model.info.v1[:] = q2; model.info.v1 -= q1; model.info.v1 /= model.grad_sim.h
+        RoboDojo.step(model.grad_sim, q2, model.info.v1, u1, 1)
+        for i in range(nq):
+            du[model.info.idx_q1[i], model.info.idx_uθ[i]] = 1.0
+        du[np.ix_(model.info.idx_q2, model.info.idx_u1)] = G(model, "∂q3∂u1")
+        du[np.ix_(model.info.idx_q2, model.info.idx_uθ1)] = G(model, "∂q3∂q1")
+        du[np.ix_(model.info.idx_q2, model.info.idx_uθ2)] = G(model, "∂q3∂q2")
+        return du
+
+    def ft(d, model, x, u, w):                                         # :104-122
+        θ = x[model.info.idx_xθ]; q1 = x[model.info.idx_q1]; q2 = x[model.info.idx_q2]; u1 = u
+        model.info.v1[:] = q2; model.info.v1 -= q1; model.info.v1 /= model.eval_sim.h
+        q3 = RoboDojo.step(model.eval_sim, q2, model.info.v1, u1, 1)
+        d[model.info.idx_q1] = q2; d[model.info.idx_q2] = q3; d[model.info.idx_xθ] = θ
+        return d
+
+    def ftx(dx, model, x, u, w):                                       # :124-148
+        nq = model.grad_sim.model.nq
+        q1 = x[model.info.idx_q1]; q2 = x[model.info.idx_q2]; u1 = u
+        model.info.v1[:] = q2; model.info.v1 -= q1; model.info.v1 /= model.grad_sim.h
+        RoboDojo.step(model.grad_sim, q2, model.info.v1, u1, 1)
+        for i in range(nq):
+            dx[model.info.idx_q1[i], model.info.idx_q2[i]] = 1.0
+        dx[np.ix_(model.info.idx_q2, model.info.idx_q1)] = G(model, "∂q3∂q1")
+        dx[np.ix_(model.info.idx_q2, model.info.idx_q2)] = G(model, "∂q3∂q2")
+        for i in model.info.idx_xθ:
+            dx[i, i] = 1.0
+        return dx
+
+    def ftu(du, model, x, u, w):                                       # :150-162
+        q1 = x[model.info.idx_q1]; q2 = x[model.info.idx_q2]; u1 = u
+        model.info.v1[:] = q2; model.info.v1 -= q1; model.info.v1 /= model.grad_sim.h
+        RoboDojo.step(model.grad_sim, q2, model.info.v1, u1, 1)
+        du[np.ix_(model.info.idx_q2, model.info.idx_u1)] = G(model, "∂q3∂u1")
+        return du
+
+    q1b, q2b, ub = od.workloads.hopper_batch(6, h=h, seed=21)
+    # the example's own initial condition (foot on the ground, standing control): examples/hopper.jl:178,270
+    q1b[0] = q2b[0] = [0.0, 0.5 + hopper.foot_radius, 0.0, 0.5]
+    ub[0] = [0.0, hopper.gravity * hopper.mass_body * 0.5 * h]
+    e = O.step_batch("hopper", q1b, q2b, ub, h, 1e-4, False)
+    g = O.step_batch("hopper", q1b, q2b, ub, h, 1e-3, True)
+    w = np.zeros(0)
+    for i in range(6):
+        if e["status"][i] or g["status"][i] or min(e["margin"][i], g["margin"][i]) < 1e-6:
+            continue
+        # stage 1: the control carries the initial state as parameters, u = [u1; q1; q2]
+        u_aug = np.concatenate([ub[i], q1b[i], q2b[i]]); x_any = np.zeros(2 * nq)
+        d = np.zeros(4 * nq); f1(d, im_dyn1, x_any, u_aug, w)
+        assert np.array_equal(d[:nq], q2b[i]) and np.abs(d[nq:2 * nq] - e["q3"][i]).max() <= Q3_TOL
+        assert np.array_equal(d[2 * nq:], u_aug[nu:])
+        du = np.zeros((4 * nq, nu + 2 * nq)); f1u(du, im_dyn1, x_any, u_aug, w)
+        assert np.abs(du[nq:2 * nq, :nu] - g["du"][i].T).max() <= GRAD_TOL
+        assert np.abs(du[nq:2 * nq, nu:nu + nq] - g["dq1"][i].T).max() <= GRAD_TOL
+        assert np.abs(du[nq:2 * nq, nu + nq:] - g["dq2"][i].T).max() <= GRAD_TOL
+        assert np.array_equal(du[:nq, nu:nu + nq], np.eye(nq)) and not du[2 * nq:].any()
+        # later stages: the state carries them, x = [q1; q2; θ]
+        x = np.concatenate([q1b[i], q2b[i], q1b[i], q2b[i]])
+        d = np.zeros(4 * nq); ft(d, im_dynt, x, ub[i], w)
+        assert np.array_equal(d[:nq], q2b[i]) and np.abs(d[nq:2 * nq] - e["q3"][i]).max() <= Q3_TOL and np.array_equal(d[2 * nq:], x[2 * nq:])
+        dx = np.zeros((4 * nq, 4 * nq)); ftx(dx, im_dynt, x, ub[i], w)
+        assert np.abs(dx[nq:2 * nq, :nq] - g["dq1"][i].T).max() <= GRAD_TOL and np.abs(dx[nq:2 * nq, nq:2 * nq] - g["dq2"][i].T).max() <= GRAD_TOL
+        assert np.array_equal(dx[:nq, nq:2 * nq], np.eye(nq)) and np.array_equal(dx[2 * nq:, 2 * nq:], np.eye(2 * nq))
+        du = np.zeros((4 * nq, nu)); ftu(du, im_dynt, x, ub[i], w)
+        assert np.abs(du[nq:2 * nq] - g["du"][i].T).max() <= GRAD_TOL and not du[:nq].any() and not du[2 * nq:].any()
+        # step!(grad_sim, …) returns the gradient simulator's own q3 (κ_grad_tol), like the reference
+        q3g = RoboDojo.step(im_dynt.grad_sim, q2b[i], (q2b[i] - q1b[i]) / h, ub[i], 1)
+        assert np.abs(q3g - g["q3"][i]).max() <= Q3_TOL and im_dynt.grad_sim.status == 0
+
+
+def test_sim_step_batch_matches_step_grad_batch(od):
+    """RoboDojo.step! call shape (q, v, u) in batch form = the (q1, q2, u) entry points on q1 = q − h·v."""
+    h = 0.05
+    q1, q2, u = od.workloads.hopper_batch(257, h=h, seed=4)
+    dyn = make_dyn(od, "hopper")
+    v = (q2 - q1) / h
+    q3e, ste = dyn.eval_sim.step_batch(q2, v, u)
+    q3, d1, d2, du, st = dyn.step_grad_batch(q1, q2, u)
+    assert np.array_equal(q3e, q3) and np.array_equal(ste, st & 15)
+    q3g, g1, g2, gu, stg = dyn.grad_sim.step_batch(q2, v, u)
+    assert np.array_equal(g1, d1) and np.array_equal(g2, d2) and np.array_equal(gu, du)
+    same = (stg == 0) & (st == 0)
+    assert same.mean() > 0.98
