@@ -51,7 +51,9 @@ typedef struct od_options {
 
 typedef struct od_handle od_handle;
 
-/* Fills *opts with the reference's settings for `model`. */
+/* Fills *opts with the settings the reference's EXAMPLES pass for `model` (κ_eval_tol 1e-4, κ_grad_tol 1e-3 / 1e-2;
+ * examples/hopper.jl:42, planar_push.jl:22).  od_create(opts = NULL) instead uses the reference CONSTRUCTOR's defaults
+ * (κ_eval_tol = κ_grad_tol = 1e-6, src/dynamics.jl:51-53). */
 int od_default_options(int model, od_options* opts);
 /* nq, nu, nz (decision variables), ntheta (data vector) of a model; any pointer may be NULL. */
 int od_model_dims(int model, int* nq, int* nu, int* nz, int* ntheta);
@@ -108,6 +110,27 @@ int od_step_grad_packed_gather_sync_device(od_handle* hd, int B, const double* i
                                            const uint64_t* gather_buffers, const uint64_t* flag_buffers, uint32_t* block_counter,
                                            uint64_t epoch, int32_t* status, int32_t* iters);
 
+/* Every variant of the fused gather through one descriptor (the two entry points above are special cases):
+ *   multicast_buffer : NVLink multicast alias of the SAME gather buffers (e.g. torch symmetric memory's multicast_ptr), or 0.
+ *                      When set, each finished 16 bytes leave as ONE multimem.st that NVSwitch replicates into every rank's buffer
+ *                      (this rank's included) instead of world−1 peer stores.  Register-path models only.
+ *   flag_buffers     : NULL = no fused barrier (caller synchronises the ranks after the kernel).
+ *   epoch / epoch_dev: epoch >= 1 = the host supplies the step's epoch;  epoch == 0 = the epoch lives in *epoch_dev (a zeroed uint64
+ *                      in this rank's device memory), advanced by one per launch on the device — such launches can sit in a CUDA
+ *                      graph and be replayed (every rank must replay the same launches).
+ *   An empty shard (B == 0) with the fused barrier still publishes / waits, so ragged splits and B_total < world do not hang. */
+typedef struct od_gather_desc {
+    int32_t world, rank;
+    int64_t row0;
+    const uint64_t* gather_buffers;
+    uint64_t multicast_buffer;
+    const uint64_t* flag_buffers;
+    uint32_t* block_counter;
+    uint64_t* epoch_dev;
+    uint64_t epoch;
+} od_gather_desc;
+int od_step_grad_packed_gather_ex_device(od_handle* hd, int B, const double* in, const od_gather_desc* gather, int32_t* status, int32_t* iters);
+
 /* Batched closed-loop rollouts — the caller of f in the outer solver: iLQR.rollout(model, x1, ū) (reference examples/cartpole.jl:79,
  * acrobot.jl:92, planar_push.jl:113, hopper.jl:272) and the forward pass / Armijo line search of IterativeLQR (step sizes down to
  * 1e-5, examples/cartpole.jl:86).  R rollouts of T knot points in ONE launch; time is sequential inside the kernel:
@@ -115,7 +138,7 @@ int od_step_grad_packed_gather_sync_device(od_handle* hd, int B, const double* i
  * x1: R×2nq initial states [q1; q2].  ubar: (T−1)×nu shared by all rollouts (ubar_per_rollout = 0) or R×(T−1)×nu.
  * xbar: T×2nq, K: (T−1)×nu×2nq row-major [t][control][state], kff: (T−1)×nu, alpha: R — each may be NULL (K needs xbar;
  * alpha NULL = 1): all NULL is the open-loop rollout.  X: R×T×2nq, U: R×(T−1)×nu (U may be NULL in the host variant),
- * status: R×(T−1) per-step solver status (0 = converged; may be NULL). */
+ * status: R×(T−1) per-step solver status (0 = converged; may be NULL).  T = 1 (no steps) returns X = x1. */
 int od_rollout_batch(od_handle* hd, int R, int T, const double* x1, const double* ubar, int ubar_per_rollout, const double* xbar,
                      const double* K, const double* kff, const double* alpha, double* X, double* U, int32_t* status);
 /* Device pointers, asynchronous; ubar_stride = doubles between the controls of consecutive rollouts (0 = shared). */
@@ -141,6 +164,18 @@ int od_riccati_batch_device(od_handle* hd, int NT, int T, const double* jac, con
  * status: OR of the statuses of the N+1 solves; 8 = singular normal equations (a coordinate never perturbed). */
 int od_bundle_batch(od_handle* hd, int B, int N, const double* eta, const double* q1, const double* q2, const double* u,
                     double* dz, int32_t* status);
+
+/* The same in pieces, device pointers, asynchronous — for device-resident callers and for sharding the sample axis over GPUs
+ * (SURVEY.md §8e): od_bundle_prepare inverts Σηηᵀ on the host (Hinv: ncol×ncol, ncol = 2nq+nu ≤ 16; non-zero = singular);
+ * od_bundle_solve_device runs the eval-sim steps p ∈ [p0, p0+P) of the flattened B×(N+1) axis (p = b·(N+1) + k, k = 0 nominal,
+ * k ≥ 1 perturbation k−1) and writes feta[p] (nq doubles) and st_work[p]; od_bundle_fit_device fits all B problems from the
+ * complete feta / st_work (e.g. after an all-gather of the slices).  eta: N×ncol and Hinv in device memory; stride_q / stride_u =
+ * doubles between consecutive rows of q1, q2 / u (0 = dense; 2nq+nu for packed rows [q1 | q2 | u]). */
+int od_bundle_prepare(int ncol, int N, const double* eta_host, double* Hinv_host);
+int od_bundle_solve_device(od_handle* hd, int B, int N, const double* eta, const double* q1, const double* q2, const double* u,
+                           int stride_q, int stride_u, long long p0, long long P, double* feta, int32_t* st_work);
+int od_bundle_fit_device(od_handle* hd, int B, int N, const double* eta, const double* Hinv, const double* feta, const int32_t* st_work,
+                         double* dz, int32_t* status);
 
 /* Rocket: f/fx/fu_rocket (proj = 0) and f/fx/fu_rocket_proj (proj = 1) — reference src/models/rocket/dynamics.jl:101-269.
  * x: B×12, u: B×3 → y: B×12, dx: B×(12×12), du: B×(12×3) column-major; dx/du may be NULL (f only).  Host pointers.

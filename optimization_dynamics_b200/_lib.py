@@ -18,6 +18,12 @@ c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
 
 
+class od_gather_desc(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("row0", C.c_int64), ("gather_buffers", C.POINTER(C.c_uint64)),
+                ("multicast_buffer", C.c_uint64), ("flag_buffers", C.POINTER(C.c_uint64)), ("block_counter", C.c_void_p),
+                ("epoch_dev", C.c_void_p), ("epoch", C.c_uint64)]
+
+
 class od_options(C.Structure):
     _fields_ = [("r_tol", C.c_double), ("kappa_eval_tol", C.c_double), ("kappa_grad_tol", C.c_double), ("ls_scale", C.c_double),
                 ("max_iter", C.c_int32), ("max_ls", C.c_int32)]
@@ -95,7 +101,11 @@ def lib():
         "od_step_grad_packed_device": (i, [vp, i, vp, vp, vp, vp, i, i]),
         "od_step_grad_packed_gather_device": (i, [vp, i, vp, C.c_longlong, i, i, C.POINTER(C.c_uint64), vp, vp]),
         "od_step_grad_packed_gather_sync_device": (i, [vp, i, vp, C.c_longlong, i, i, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), vp, C.c_uint64, vp, vp]),
+        "od_step_grad_packed_gather_ex_device": (i, [vp, i, vp, C.POINTER(od_gather_desc), vp, vp]),
         "od_bundle_batch": (i, [vp, i, i, dp, dp, dp, dp, dp, ip]),
+        "od_bundle_prepare": (i, [i, i, dp, dp]),
+        "od_bundle_solve_device": (i, [vp, i, i, vp, vp, vp, vp, i, i, C.c_longlong, C.c_longlong, vp, vp]),
+        "od_bundle_fit_device": (i, [vp, i, i, vp, vp, vp, vp, vp, vp]),
         "od_riccati_batch": (i, [vp, i, i, dp, dp, dp, dp, dp, dp, d, dp, dp, dp, ip]),
         "od_riccati_batch_device": (i, [vp, i, i, vp, vp, vp, vp, vp, vp, d, vp, vp, vp, vp]),
         "od_rollout_batch": (i, [vp, i, i, dp, dp, i, dp, dp, dp, dp, dp, dp, ip]),
@@ -116,7 +126,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = ["od_default_options", "od_model_dims", "od_create", "od_destroy", "od_set_stream", "od_synchronize", "od_step_batch",
-                    "od_step_grad_batch", "od_step_grad_packed", "od_sim_step_batch", "od_step_grad_batch_device", "od_step_grad_packed_device", "od_step_grad_packed_gather_device", "od_step_grad_packed_gather_sync_device", "od_bundle_batch",
+                    "od_step_grad_batch", "od_step_grad_packed", "od_sim_step_batch", "od_step_grad_batch_device", "od_step_grad_packed_device", "od_step_grad_packed_gather_device", "od_step_grad_packed_gather_sync_device", "od_step_grad_packed_gather_ex_device", "od_bundle_batch", "od_bundle_prepare", "od_bundle_solve_device", "od_bundle_fit_device",
                     "od_rollout_batch", "od_rollout_batch_device", "od_riccati_batch", "od_riccati_batch_device",
                     "od_rocket_batch", "od_rocket_batch_device", "od_rocket_projection_batch", "od_launch_count", "od_last_error", "od_version"]
 

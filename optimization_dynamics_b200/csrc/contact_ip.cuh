@@ -842,6 +842,7 @@ struct StepArgs {
     // gradient bundle (reference src/gradient_bundle.jl:89-100): problem i = sample i/(n_eta+1) perturbed by eta row i%(n_eta+1) − 1
     // (row −1 = nominal); eta is n_eta × (2NQ+NU), null when unused.
     const double* eta; int n_eta;
+    long long eta_i0;          // index of this launch's first problem on the flattened (sample × perturbation) axis (multi-GPU slices)
     // Fused all-gather (multi-GPU): when n_peers > 1 the packed output row of problem i is also stored into the gather buffers of
     // the other ranks (peer-mapped device pointers, NVLink P2P) as soon as the problem has finished — the transfer overlaps the
     // remaining problems' compute and replaces the separate ncclAllGather.  `gather_row0` = first row of this rank's shard,
@@ -863,6 +864,12 @@ struct StepArgs {
     unsigned long long* sync_flags[8];
     unsigned int* sync_counter;
     unsigned long long sync_epoch;
+    // sync_epoch == 0: the epoch lives on the device — sync_epoch_dev (this rank's u64, zero before the first launch) is advanced by
+    // one per launch by the last block, so a CUDA graph holding such launches can be replayed (every rank replays the same launches).
+    unsigned long long* sync_epoch_dev;
+    // NVLink multicast alias of the gather buffers (torch symmetric memory multicast_ptr; null = per-peer stores): ONE multimem.st
+    // per 16 bytes reaches the gather buffer of every rank — this one included — and NVSwitch does the replication.
+    double* mc_out;
     SolverOpts opts;
 };
 
@@ -893,8 +900,9 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
     double th[M::NTH];
     typename IP::Z z, D, zc;
     {
-        const int src = a.eta ? i / (a.n_eta + 1) : i;
-        const int pert = a.eta ? i % (a.n_eta + 1) : 0;
+        const long long ig = a.eta ? a.eta_i0 + i : i;
+        const int src = a.eta ? (int)(ig / (a.n_eta + 1)) : i;
+        const int pert = a.eta ? (int)(ig % (a.n_eta + 1)) : 0;
         const double* p1 = a.q1 + (size_t)src * a.in_stride_q;
         const double* p2 = a.q2 + (size_t)src * a.in_stride_q;
         const double* pu = a.u + (size_t)src * a.in_stride_u;
@@ -1054,12 +1062,22 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
                 const int e = g + G * t;
                 if (G == 1 || e < NOUT / 2) {
                     const double2 v = src[e];
-                    dst[e] = v;
 #ifdef __CUDA_ARCH__
-                    if (a.n_peers > 1) {
+                    if (a.n_peers > 1 && a.mc_out) {
+                        // one multicast store: every rank's gather buffer (this rank's too) receives the 16 bytes
                         const size_t off = ((size_t)(a.gather_row0 + i) * a.gather_width) / 2 + e;
-                        for (int p = 0; p < a.n_peers; ++p) if (p != a.self_rank) reinterpret_cast<double2*>(a.peer_out[p])[off] = v;
+                        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(reinterpret_cast<double2*>(a.mc_out) + off),
+                                     "f"(__int_as_float(__double2loint(v.x))), "f"(__int_as_float(__double2hiint(v.x))),
+                                     "f"(__int_as_float(__double2loint(v.y))), "f"(__int_as_float(__double2hiint(v.y))) : "memory");
+                    } else {
+                        dst[e] = v;
+                        if (a.n_peers > 1) {
+                            const size_t off = ((size_t)(a.gather_row0 + i) * a.gather_width) / 2 + e;
+                            for (int p = 0; p < a.n_peers; ++p) if (p != a.self_rank) reinterpret_cast<double2*>(a.peer_out[p])[off] = v;
+                        }
                     }
+#else
+                    dst[e] = v;
 #endif
                 }
             }
@@ -1082,6 +1100,22 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
             }
         }
         }
+#ifdef __CUDA_ARCH__
+        if constexpr (M::ROBUST_IFT) {
+            // fused all-gather: the rank-revealing IFT wrote the Jacobian blocks of the LOCAL row itself (lane 0, straight to global
+            // memory) and only q3 went through the staged row above — forward the rest of the row to the peers from this rank's own
+            // gather buffer, as the shared-memory-LU path does
+            if (a.n_peers > 1 && a.want_grad && a.dq1) {
+                L.sync();                                          // lane 0's stores to the local row are visible to the group
+                const size_t off = (size_t)(a.gather_row0 + i) * a.gather_width;
+                const double* row = a.peer_out[a.self_rank] + off;
+                for (int k = NQ + g; k < a.gather_width; k += G) {
+                    const double v = __ldcg(row + k);
+                    for (int p = 0; p < a.n_peers; ++p) if (p != a.self_rank) a.peer_out[p][off + k] = v;
+                }
+            }
+        }
+#endif
     } else {
         if (a.want_grad && a.dq1) {
             IP::load_z(L, z);
@@ -1129,23 +1163,42 @@ __global__ void __launch_bounds__(G * PPB, OD_MIN_BLOCKS) contact_step_kernel(co
     if (i >= a.B) i = a.B - 1;               // padding lanes of the last warp repeat the last problem (identical values, same addresses)
     contact_step_one<M, G, PPB, REG>(a, i, od_smem + slot * ContactIP<M, G, PPB, REG>::WS_SLOT, g, 0xffffffffu);
     if (a.sync_counter) {                                   // fused cross-GPU barrier (see StepArgs)
-        __threadfence_system();                             // this thread's peer stores are performed before the block is counted
+        // The block barrier orders every thread's peer / multicast stores before thread 0's system-scope fence, which is cumulative
+        // (the pattern of cooperative-groups grid sync: bar.sync, then ONE thread fences and signals) — one fence per block, not per thread.
         __syncthreads();
         if (threadIdx.x == 0) {
+            __threadfence_system();
             const unsigned prev = atomicAdd(a.sync_counter, 1u);
             if (prev == gridDim.x - 1) {                    // last block of this rank: every row of the shard is on its way / there
                 *a.sync_counter = 0u;                       // ready for the next launch (stream-ordered)
                 __threadfence_system();
+                const unsigned long long epoch = a.sync_epoch ? a.sync_epoch : *a.sync_epoch_dev + 1ull;
                 for (int p = 0; p < a.n_peers; ++p)
-                    if (p != a.self_rank) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.sync_flags[p] + a.self_rank), "l"(a.sync_epoch) : "memory");
+                    if (p != a.self_rank) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.sync_flags[p] + a.self_rank), "l"(epoch) : "memory");
                 for (int p = 0; p < a.n_peers; ++p) {
                     if (p == a.self_rank) continue;
                     unsigned long long v;
-                    do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.sync_flags[a.self_rank] + p) : "memory"); } while (v < a.sync_epoch);
+                    do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.sync_flags[a.self_rank] + p) : "memory"); } while (v < epoch);
                 }
+                if (!a.sync_epoch) *a.sync_epoch_dev = epoch;
             }
         }
     }
+}
+
+// A rank whose shard is empty still has to take part in the fused cross-GPU barrier: publish the epoch, wait for the peers.
+static __global__ void gather_sync_only_kernel(const StepArgs a) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    __threadfence_system();
+    const unsigned long long epoch = a.sync_epoch ? a.sync_epoch : *a.sync_epoch_dev + 1ull;
+    for (int p = 0; p < a.n_peers; ++p)
+        if (p != a.self_rank) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.sync_flags[p] + a.self_rank), "l"(epoch) : "memory");
+    for (int p = 0; p < a.n_peers; ++p) {
+        if (p == a.self_rank) continue;
+        unsigned long long v;
+        do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.sync_flags[a.self_rank] + p) : "memory"); } while (v < epoch);
+    }
+    if (!a.sync_epoch) *a.sync_epoch_dev = epoch;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1186,9 +1239,9 @@ OD_HD void contact_rollout_one(const RolloutArgs& ra, const int r, double* ws, c
     a.h = ra.h;
 #pragma unroll
     for (int k = 0; k < 4; ++k) a.fric[k] = ra.fric[k];
-    a.want_eval = 1; a.want_grad = 0; a.eta = nullptr; a.n_eta = 0;
+    a.want_eval = 1; a.want_grad = 0; a.eta = nullptr; a.n_eta = 0; a.eta_i0 = 0;
     a.n_peers = 0; a.self_rank = 0; a.gather_row0 = 0; a.gather_width = 0;
-    a.packed_out = 0; a.in_packed = 0; a.in_vel = 0; a.sync_counter = nullptr; a.sync_epoch = 0;
+    a.packed_out = 0; a.in_packed = 0; a.in_vel = 0; a.sync_counter = nullptr; a.sync_epoch = 0; a.sync_epoch_dev = nullptr; a.mc_out = nullptr;
     a.opts = ra.opts;
     const double alpha = ra.alpha ? ra.alpha[r] : 1.0;
     const double* ub = ra.ubar + (size_t)r * ra.ubar_stride;

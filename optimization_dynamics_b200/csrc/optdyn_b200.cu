@@ -142,7 +142,13 @@ od_handle* od_create(int model, double h, const od_options* opts, const double* 
     od_handle* hd = new (std::nothrow) od_handle();
     if (!hd) { fail("od_create: out of memory"); return nullptr; }
     hd->model = model; hd->device = device; hd->h = h; hd->launches = 0;
-    if (opts) hd->opts = *opts; else od_default_options(model, &hd->opts);
+    if (opts) hd->opts = *opts;
+    else {
+        od_default_options(model, &hd->opts);
+        // NULL = the reference CONSTRUCTOR's defaults, ImplicitDynamics(...; r_tol=1e-8, κ_eval_tol=1e-6, κ_grad_tol=1e-6) (src/dynamics.jl:51-53);
+        // od_default_options() holds the looser values the reference's EXAMPLES pass.  The rocket keeps RocketInfo's own settings.
+        if (model != OD_ROCKET) { hd->opts.kappa_eval_tol = 1e-6; hd->opts.kappa_grad_tol = 1e-6; }
+    }
     for (int k = 0; k < 4; ++k) hd->params[k] = 0.0;
     if (model == OD_CARTPOLE_FRICTION) { hd->params[0] = 0.1; hd->params[1] = 0.1; }      // cartpole/model.jl:132
     if (model == OD_HOPPER) { hd->params[0] = 0.5; hd->params[1] = 0.5; }                 // DESIGN.md §Hopper constants
@@ -243,49 +249,64 @@ int od_step_grad_packed_device(od_handle* hd, int B, const double* in, double* o
     return launch_step(hd, a);
 }
 
-int od_step_grad_packed_gather_device(od_handle* hd, int B, const double* in, long long row0, int world, int rank,
-                                      const uint64_t* gather_buffers, int32_t* status, int32_t* iters) {
+// Multi-GPU derivative sweep, every variant (see od_gather_desc in the header)
+int od_step_grad_packed_gather_ex_device(od_handle* hd, int B, const double* in, const od_gather_desc* g, int32_t* status, int32_t* iters) {
     if (!hd) return fail("null handle");
-    if (world < 1 || world > 8 || rank < 0 || rank >= world || !gather_buffers) return fail("od_step_grad_packed_gather_device: need 1 <= world <= 8 and the peer buffer table");
+    if (!g || g->world < 1 || g->world > 8 || g->rank < 0 || g->rank >= g->world || !g->gather_buffers)
+        return fail("od_step_grad_packed_gather: need 1 <= world <= 8 and the peer buffer table");
+    const bool sync = g->flag_buffers != nullptr;
+    if (sync && (!g->block_counter || (g->epoch == 0 && !g->epoch_dev)))
+        return fail("od_step_grad_packed_gather: the fused barrier needs the flag table, a block counter and an epoch (value >= 1 or device counter)");
+    if (hd->model == OD_ROCKET) return fail("od_step_grad_packed_gather: contact models only");
+    if ((sync || g->multicast_buffer) && !rows_leave_coalesced(hd->model, B > 0 ? B : 1))
+        return fail("od_step_grad_packed_gather: the fused barrier / multicast stores need the cooperative-lane register path (hopper, cartpole, acrobot)");
     Dims d; dims_of(hd->model, &d);
     OD_CUDA(cudaSetDevice(hd->device));
     const int inw = 2 * d.nq + d.nu, outw = d.nq + d.nq * inw;
-    double* out = (double*)gather_buffers[rank] + (size_t)row0 * outw;
+    double* out = (double*)g->gather_buffers[g->rank] + (size_t)g->row0 * outw;
     StepArgs a; memset(&a, 0, sizeof(a));
     a.B = B; a.q1 = in; a.q2 = in + d.nq; a.u = in + 2 * d.nq; a.in_stride_q = inw; a.in_stride_u = inw; a.in_packed = 1;
     a.q3 = out; a.dq1 = out + d.nq; a.dq2 = out + d.nq + d.nq * d.nq; a.du = out + d.nq + 2 * d.nq * d.nq;
     a.out_stride_q3 = outw; a.out_stride_dq = outw; a.out_stride_du = outw;
     a.status = status; a.iters = iters; a.want_eval = 1; a.want_grad = 1;
-    a.n_peers = world; a.self_rank = rank; a.gather_row0 = row0; a.gather_width = outw;
-    for (int r = 0; r < world; ++r) a.peer_out[r] = (double*)gather_buffers[r];
-    bool aligned = true;
-    for (int r = 0; r < world; ++r) aligned = aligned && ((gather_buffers[r] & 15) == 0);
+    a.n_peers = g->world; a.self_rank = g->rank; a.gather_row0 = g->row0; a.gather_width = outw;
+    bool aligned = (g->multicast_buffer & 15) == 0;
+    for (int r = 0; r < g->world; ++r) {
+        a.peer_out[r] = (double*)g->gather_buffers[r];
+        aligned = aligned && ((g->gather_buffers[r] & 15) == 0);
+        if (sync) a.sync_flags[r] = (unsigned long long*)g->flag_buffers[r];
+    }
     a.packed_out = aligned ? 1 : 0;
+    a.mc_out = (aligned && outw % 2 == 0) ? (double*)g->multicast_buffer : nullptr;
+    if (sync) { a.sync_counter = g->block_counter; a.sync_epoch = g->epoch; a.sync_epoch_dev = (unsigned long long*)g->epoch_dev; }
+    if (B <= 0) {
+        if (!sync) return 0;
+        // empty shard (ragged split, B_total < world): the peers still wait for this rank's flag
+        gather_sync_only_kernel<<<1, 32, 0, hd->stream>>>(a);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail("gather_sync_only_kernel launch", e);
+        hd->launches++;
+        return 0;
+    }
     return launch_step(hd, a);
+}
+
+int od_step_grad_packed_gather_device(od_handle* hd, int B, const double* in, long long row0, int world, int rank,
+                                      const uint64_t* gather_buffers, int32_t* status, int32_t* iters) {
+    od_gather_desc g; memset(&g, 0, sizeof(g));
+    g.world = world; g.rank = rank; g.row0 = row0; g.gather_buffers = gather_buffers;
+    return od_step_grad_packed_gather_ex_device(hd, B, in, &g, status, iters);
 }
 
 int od_step_grad_packed_gather_sync_device(od_handle* hd, int B, const double* in, long long row0, int world, int rank,
                                            const uint64_t* gather_buffers, const uint64_t* flag_buffers, uint32_t* block_counter,
                                            uint64_t epoch, int32_t* status, int32_t* iters) {
-    if (!hd) return fail("null handle");
-    if (world < 1 || world > 8 || rank < 0 || rank >= world || !gather_buffers || !flag_buffers || !block_counter || epoch == 0)
+    if (!flag_buffers || !block_counter || epoch == 0)
         return fail("od_step_grad_packed_gather_sync_device: need 1 <= world <= 8, the peer buffer and flag tables, a block counter and epoch >= 1");
-    if (!rows_leave_coalesced(hd->model, B)) return fail("od_step_grad_packed_gather_sync_device: needs the cooperative-lane register path (hopper, cartpole, acrobot)");
-    Dims d; dims_of(hd->model, &d);
-    OD_CUDA(cudaSetDevice(hd->device));
-    const int inw = 2 * d.nq + d.nu, outw = d.nq + d.nq * inw;
-    double* out = (double*)gather_buffers[rank] + (size_t)row0 * outw;
-    StepArgs a; memset(&a, 0, sizeof(a));
-    a.B = B; a.q1 = in; a.q2 = in + d.nq; a.u = in + 2 * d.nq; a.in_stride_q = inw; a.in_stride_u = inw; a.in_packed = 1;
-    a.q3 = out; a.dq1 = out + d.nq; a.dq2 = out + d.nq + d.nq * d.nq; a.du = out + d.nq + 2 * d.nq * d.nq;
-    a.out_stride_q3 = outw; a.out_stride_dq = outw; a.out_stride_du = outw;
-    a.status = status; a.iters = iters; a.want_eval = 1; a.want_grad = 1;
-    a.n_peers = world; a.self_rank = rank; a.gather_row0 = row0; a.gather_width = outw;
-    bool aligned = true;
-    for (int r = 0; r < world; ++r) { a.peer_out[r] = (double*)gather_buffers[r]; a.sync_flags[r] = (unsigned long long*)flag_buffers[r]; aligned = aligned && ((gather_buffers[r] & 15) == 0); }
-    a.packed_out = aligned ? 1 : 0;
-    a.sync_counter = block_counter; a.sync_epoch = epoch;
-    return launch_step(hd, a);
+    od_gather_desc g; memset(&g, 0, sizeof(g));
+    g.world = world; g.rank = rank; g.row0 = row0; g.gather_buffers = gather_buffers; g.flag_buffers = flag_buffers;
+    g.block_counter = block_counter; g.epoch = epoch;
+    return od_step_grad_packed_gather_ex_device(hd, B, in, &g, status, iters);
 }
 
 // Device-visible alias of a pinned (page-locked, mapped) host buffer, or null for pageable memory (queried on every call: a
@@ -430,7 +451,14 @@ int od_rollout_batch_device(od_handle* hd, int R, int T, const double* x1, const
                             const double* K, const double* kff, const double* alpha, double* X, double* U, int32_t* status, int32_t* iters) {
     if (!hd) return fail("null handle");
     if (hd->model == OD_ROCKET) return fail("od_rollout_batch: contact models only");
-    if (R <= 0 || T <= 1) return 0;
+    if (R <= 0 || T <= 0) return 0;
+    if (T == 1) {                              // zero steps: the rollout is [x1], like iLQR.rollout with an empty control sequence
+        if (!x1 || !X) return fail("od_rollout_batch: x1 and X are required");
+        Dims d1; dims_of(hd->model, &d1);
+        OD_CUDA(cudaSetDevice(hd->device));
+        OD_CUDA(cudaMemcpyAsync(X, x1, sizeof(double) * 2 * d1.nq * (size_t)R, cudaMemcpyDeviceToDevice, hd->stream));
+        return 0;
+    }
     if (!x1 || !ubar || !X || !U) return fail("od_rollout_batch: x1, ubar, X and U are required");
     if (K && !xbar) return fail("od_rollout_batch: feedback gains K need the nominal states xbar");
     OD_CUDA(cudaSetDevice(hd->device));
@@ -460,7 +488,12 @@ int od_rollout_batch(od_handle* hd, int R, int T, const double* x1, const double
     if (!hd) return fail("null handle");
     Dims d; dims_of(hd->model, &d);
     if (hd->model == OD_ROCKET) return fail("od_rollout_batch: contact models only");
-    if (R <= 0 || T <= 1) return 0;
+    if (R <= 0 || T <= 0) return 0;
+    if (T == 1) {
+        if (!x1 || !X) return fail("od_rollout_batch: x1 and X are required");
+        memcpy(X, x1, sizeof(double) * 2 * d.nq * (size_t)R);
+        return 0;
+    }
     if (!x1 || !ubar || !X) return fail("od_rollout_batch: x1, ubar and X are required");
     if (K && !xbar) return fail("od_rollout_batch: feedback gains K need the nominal states xbar");
     OD_CUDA(cudaSetDevice(hd->device));
@@ -548,24 +581,18 @@ int od_riccati_batch(od_handle* hd, int NT, int T, const double* jac, const doub
     return 0;
 }
 
-int od_bundle_batch(od_handle* hd, int B, int N, const double* eta, const double* q1, const double* q2, const double* u, double* dz, int32_t* status) {
-    if (!hd) return fail("null handle");
-    Dims d; dims_of(hd->model, &d);
-    if (hd->model == OD_ROCKET) return fail("od_bundle_batch: contact models only");
-    if (B <= 0) return 0;
-    if (N <= 0 || !eta || !dz) return fail("od_bundle_batch: need N > 0, eta and dz");
-    const int nq = d.nq, nu = d.nu, ncol = 2 * nq + nu;
-    if (ncol > 16) return fail("od_bundle_batch: 2nq+nu > 16 unsupported");
-    // H = Σ η ηᵀ, inverted on the host by Gauss–Jordan with partial pivoting (ncol ≤ 12)
-    double H[16 * 16], Hi[16 * 16];
+// H = Σ η ηᵀ inverted on the host by Gauss–Jordan with partial pivoting (ncol ≤ 16); returns non-zero when singular
+int od_bundle_prepare(int ncol, int N, const double* eta, double* Hinv) {
+    if (ncol <= 0 || ncol > 16 || N <= 0 || !eta || !Hinv) return fail("od_bundle_prepare: need 0 < 2nq+nu <= 16, N > 0, eta and Hinv");
+    double H[16 * 16]; double* Hi = Hinv;
     for (int i = 0; i < ncol * ncol; ++i) { H[i] = 0.0; Hi[i] = 0.0; }
     for (int k = 0; k < N; ++k) for (int i = 0; i < ncol; ++i) for (int j = 0; j < ncol; ++j) H[i * ncol + j] += eta[(size_t)k * ncol + i] * eta[(size_t)k * ncol + j];
     for (int i = 0; i < ncol; ++i) Hi[i * ncol + i] = 1.0;
-    bool singular = false;
-    for (int k = 0; k < ncol && !singular; ++k) {
+    for (int k = 0; k < ncol; ++k) {
         int p = k; double best = fabs(H[k * ncol + k]);
         for (int i = k + 1; i < ncol; ++i) if (fabs(H[i * ncol + k]) > best) { best = fabs(H[i * ncol + k]); p = i; }
-        if (!(best > 0.0)) { singular = true; break; }
+        // the reference's LU would divide by zero here (a coordinate that no perturbation touches)
+        if (!(best > 0.0)) return fail("od_bundle: Σηηᵀ is singular (some coordinate is never perturbed)");
         if (p != k) for (int j = 0; j < ncol; ++j) { double t = H[k * ncol + j]; H[k * ncol + j] = H[p * ncol + j]; H[p * ncol + j] = t; t = Hi[k * ncol + j]; Hi[k * ncol + j] = Hi[p * ncol + j]; Hi[p * ncol + j] = t; }
         const double inv = 1.0 / H[k * ncol + k];
         for (int j = 0; j < ncol; ++j) { H[k * ncol + j] *= inv; Hi[k * ncol + j] *= inv; }
@@ -574,9 +601,48 @@ int od_bundle_batch(od_handle* hd, int B, int N, const double* eta, const double
             if (l != 0.0) for (int j = 0; j < ncol; ++j) { H[i * ncol + j] -= l * H[k * ncol + j]; Hi[i * ncol + j] -= l * Hi[k * ncol + j]; }
         }
     }
-    if (singular) {   // the reference's LU would divide by zero here (a coordinate that no perturbation touches)
+    return 0;
+}
+
+int od_bundle_solve_device(od_handle* hd, int B, int N, const double* eta, const double* q1, const double* q2, const double* u,
+                           int stride_q, int stride_u, long long p0, long long P, double* feta, int32_t* st_work) {
+    if (!hd) return fail("null handle");
+    Dims d; dims_of(hd->model, &d);
+    if (hd->model == OD_ROCKET) return fail("od_bundle: contact models only");
+    if (P <= 0) return 0;
+    if (N <= 0 || !eta || !feta || !st_work || p0 < 0 || p0 + P > (long long)B * (N + 1)) return fail("od_bundle_solve_device: bad arguments");
+    OD_CUDA(cudaSetDevice(hd->device));
+    StepArgs a; memset(&a, 0, sizeof(a));
+    a.B = (int)P; a.q1 = q1; a.q2 = q2; a.u = u; a.in_stride_q = stride_q > 0 ? stride_q : d.nq; a.in_stride_u = stride_u > 0 ? stride_u : d.nu;
+    a.q3 = feta + (size_t)p0 * d.nq; a.out_stride_q3 = d.nq; a.status = st_work + p0; a.want_eval = 1; a.want_grad = 0; a.eta = eta; a.n_eta = N; a.eta_i0 = p0;
+    return launch_step(hd, a);
+}
+
+int od_bundle_fit_device(od_handle* hd, int B, int N, const double* eta, const double* Hinv, const double* feta, const int32_t* st_work,
+                         double* dz, int32_t* status) {
+    if (!hd) return fail("null handle");
+    Dims d; dims_of(hd->model, &d);
+    if (B <= 0) return 0;
+    if (N <= 0 || !eta || !Hinv || !feta || !st_work || !dz) return fail("od_bundle_fit_device: bad arguments");
+    OD_CUDA(cudaSetDevice(hd->device));
+    bundle_fit_kernel<<<(B + 63) / 64, 64, 0, hd->stream>>>(B, N, d.nq, 2 * d.nq + d.nu, feta, eta, Hinv, st_work, dz, status);
+    OD_CUDA(cudaGetLastError());
+    hd->launches++;
+    return 0;
+}
+
+int od_bundle_batch(od_handle* hd, int B, int N, const double* eta, const double* q1, const double* q2, const double* u, double* dz, int32_t* status) {
+    if (!hd) return fail("null handle");
+    Dims d; dims_of(hd->model, &d);
+    if (hd->model == OD_ROCKET) return fail("od_bundle_batch: contact models only");
+    if (B <= 0) return 0;
+    if (N <= 0 || !eta || !dz) return fail("od_bundle_batch: need N > 0, eta and dz");
+    const int nq = d.nq, nu = d.nu, ncol = 2 * nq + nu;
+    if (ncol > 16) return fail("od_bundle_batch: 2nq+nu > 16 unsupported");
+    double Hi[16 * 16];
+    if (od_bundle_prepare(ncol, N, eta, Hi)) {
         if (status) for (int b = 0; b < B; ++b) status[b] = 8;
-        return fail("od_bundle_batch: Σηηᵀ is singular (some coordinate is never perturbed)");
+        return 1;
     }
     OD_CUDA(cudaSetDevice(hd->device));
     const size_t P = (size_t)B * (N + 1);
@@ -595,13 +661,8 @@ int od_bundle_batch(od_handle* hd, int B, int N, const double* eta, const double
     OD_CUDA(cudaMemcpyAsync(d_u, u, sizeof(double) * nu * B, cudaMemcpyHostToDevice, hd->stream));
     OD_CUDA(cudaMemcpyAsync(d_eta, eta, sizeof(double) * N * ncol, cudaMemcpyHostToDevice, hd->stream));
     OD_CUDA(cudaMemcpyAsync(d_Hi, Hi, sizeof(double) * ncol * ncol, cudaMemcpyHostToDevice, hd->stream));
-    StepArgs a; memset(&a, 0, sizeof(a));
-    a.B = (int)P; a.q1 = d_q1; a.q2 = d_q2; a.u = d_u; a.in_stride_q = nq; a.in_stride_u = nu;
-    a.q3 = d_f; a.out_stride_q3 = nq; a.status = d_st; a.want_eval = 1; a.want_grad = 0; a.eta = d_eta; a.n_eta = N;
-    if (launch_step(hd, a)) return 1;
-    bundle_fit_kernel<<<(B + 63) / 64, 64, 0, hd->stream>>>(B, N, nq, ncol, d_f, d_eta, d_Hi, d_st, (double*)hd->out.p, (int32_t*)hd->st.p);
-    OD_CUDA(cudaGetLastError());
-    hd->launches++;
+    if (od_bundle_solve_device(hd, B, N, d_eta, d_q1, d_q2, d_u, 0, 0, 0, (long long)P, d_f, d_st)) return 1;
+    if (od_bundle_fit_device(hd, B, N, d_eta, d_Hi, d_f, d_st, (double*)hd->out.p, (int32_t*)hd->st.p)) return 1;
     OD_CUDA(cudaMemcpyAsync(dz, hd->out.p, sizeof(double) * (size_t)B * nq * ncol, cudaMemcpyDeviceToHost, hd->stream));
     if (status) OD_CUDA(cudaMemcpyAsync(status, hd->st.p, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, hd->stream));
     OD_CUDA(cudaStreamSynchronize(hd->stream));
