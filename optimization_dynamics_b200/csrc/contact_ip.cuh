@@ -708,7 +708,7 @@ struct ContactIP {
     // At a sticking iterate with κ → 0 the friction multipliers are not unique and rz is numerically rank deficient, while the
     // q rows of δz stay well defined.  Partial pivoting then divides by rounding-level pivots (or hits an exact zero); here the
     // factorisation at the final iterate uses COMPLETE pivoting, stops at the numerical rank, and solves the consistent system
-    // with the free multipliers set to zero.  Runs once per problem, on lane 0 of the group (dynamic loops: small code).
+    // with the free multipliers set to zero.  Runs once per problem, on all lanes of the group (dynamic loops: small code).
     OD_HD static bool sensitivities_robust(Lin& L, const Z& z, const double* th, const double* trc, const double* trv, double* dq1, double* dq2, double* du) {
         {
             double Dth[NQ * NTP], Vth[NB1 * NTP];
@@ -733,23 +733,38 @@ struct ContactIP {
             }
         }
         L.sync();
+        // All G lanes of the group work on the shared-memory system: the pivot search scans rows g, g+G, … per lane and combines by
+        // shuffle (largest magnitude, first in row-major order among equals — the choice a sequential scan makes), interchanges are
+        // split by column / row, the elimination by row, the back-substitution by right-hand side.  Every element sees the same
+        // operations in the same order as with one lane, so the result does not depend on G.  The groups of a warp run in lockstep
+        // (full-mask shuffles): a group that has reached its numerical rank idles through the remaining steps.
+        double amax = 0.0;
+        for (int i = L.g; i < NR; i += G) for (int j = 0; j < NR; ++j) amax = fmax(amax, fabs(L.K(i, j)));
+        { int dummy = 0; Grp<G>::argmax_all(amax, dummy, L.gmask); }
+        const double tol = 1e-13 * amax;      // exact redundancy leaves pivots at rounding level (≲1e-16·amax); κ-level pivots (≳1e-11) are genuine
         int rank = NR;
-        if (L.g == 0) {
-            double amax = 0.0;
-            for (int i = 0; i < NR; ++i) for (int j = 0; j < NR; ++j) amax = fmax(amax, fabs(L.K(i, j)));
-            const double tol = 1e-13 * amax;      // exact redundancy leaves pivots at rounding level (≲1e-16·amax); κ-level pivots (≳1e-11) are genuine
-            for (int k = 0; k < NR; ++k) {
-                int p = k, q = k; double best = -1.0;
-                for (int i = k; i < NR; ++i) for (int j = k; j < NR; ++j) { const double a = fabs(L.K(i, j)); if (a > best) { best = a; p = i; q = j; } }
-                if (!(best > tol)) { rank = k; break; }
-                L.CP(k) = (double)q;
+        for (int k = 0; k < NR; ++k) {
+            const bool live = rank == NR;     // false once the numerical rank has been found
+            double best = -1.0; int at = k * NR + k;
+            if (live)
+                for (int i = k + L.g; i < NR; i += G) for (int j = k; j < NR; ++j) { const double a = fabs(L.K(i, j)); if (a > best) { best = a; at = i * NR + j; } }
+            Grp<G>::argmax_all(best, at, L.gmask);
+            if (live && !(best > tol)) rank = k;
+            const bool go = rank == NR;
+            const int p = at / NR, q = at % NR;
+            if (go) {
+                if (L.g == 0) L.CP(k) = (double)q;
                 if (p != k) {
-                    for (int j = 0; j < NR; ++j) { const double t = L.K(k, j); L.K(k, j) = L.K(p, j); L.K(p, j) = t; }
-                    for (int c = 0; c < NTP; ++c) { const double t = L.X(c, k); L.X(c, k) = L.X(c, p); L.X(c, p) = t; }     // row swap applied to every rhs
+                    for (int j = L.g; j < NR; j += G) { const double t = L.K(k, j); L.K(k, j) = L.K(p, j); L.K(p, j) = t; }
+                    for (int c = L.g; c < NTP; c += G) { const double t = L.X(c, k); L.X(c, k) = L.X(c, p); L.X(c, p) = t; }     // row swap applied to every rhs
                 }
-                if (q != k) for (int i = 0; i < NR; ++i) { const double t = L.K(i, k); L.K(i, k) = L.K(i, q); L.K(i, q) = t; }
+            }
+            L.sync();
+            if (go && q != k) for (int i = L.g; i < NR; i += G) { const double t = L.K(i, k); L.K(i, k) = L.K(i, q); L.K(i, q) = t; }
+            L.sync();
+            if (go) {
                 const double inv = 1.0 / L.K(k, k);
-                for (int i = k + 1; i < NR; ++i) {
+                for (int i = k + 1 + L.g; i < NR; i += G) {
                     const double l = L.K(i, k) * inv;
                     if (l != 0.0) {
                         for (int j = k + 1; j < NR; ++j) L.K(i, j) -= l * L.K(k, j);
@@ -757,17 +772,18 @@ struct ContactIP {
                     }
                 }
             }
-            for (int c = 0; c < NTP; ++c) {
-                for (int i = rank; i < NR; ++i) L.X(c, i) = 0.0;                                  // free (non-unique) unknowns
-                for (int i = rank - 1; i >= 0; --i) {
-                    double sacc = L.X(c, i);
-                    for (int j = i + 1; j < rank; ++j) sacc -= L.K(i, j) * L.X(c, j);
-                    L.X(c, i) = sacc / L.K(i, i);
-                }
-                for (int k = rank - 1; k >= 0; --k) { const int q = (int)L.CP(k); if (q != k) { const double t = L.X(c, k); L.X(c, k) = L.X(c, q); L.X(c, q) = t; } }
-                double* dst = (c < NQ) ? (dq1 + c * NQ) : (c < 2 * NQ) ? (dq2 + (c - NQ) * NQ) : (du + (c - 2 * NQ) * NQ);
-                for (int i = 0; i < NQ; ++i) dst[i] = -L.X(c, i);
+            L.sync();
+        }
+        for (int c = L.g; c < NTP; c += G) {
+            for (int i = rank; i < NR; ++i) L.X(c, i) = 0.0;                                  // free (non-unique) unknowns
+            for (int i = rank - 1; i >= 0; --i) {
+                double sacc = L.X(c, i);
+                for (int j = i + 1; j < rank; ++j) sacc -= L.K(i, j) * L.X(c, j);
+                L.X(c, i) = sacc / L.K(i, i);
             }
+            for (int k = rank - 1; k >= 0; --k) { const int q = (int)L.CP(k); if (q != k) { const double t = L.X(c, k); L.X(c, k) = L.X(c, q); L.X(c, q) = t; } }
+            double* dst = (c < NQ) ? (dq1 + c * NQ) : (c < 2 * NQ) ? (dq2 + (c - NQ) * NQ) : (du + (c - 2 * NQ) * NQ);
+            for (int i = 0; i < NQ; ++i) dst[i] = -L.X(c, i);
         }
         L.sync();
         return rank > 0;

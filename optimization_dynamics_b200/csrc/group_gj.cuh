@@ -70,6 +70,22 @@ template <int G> struct Grp {
 #endif
         return v;
     }
+    // (largest value, smallest index among equals) over the lanes of the group, replicated in every lane
+    OD_HD static void argmax_all(double& best, int& idx, unsigned m) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+        for (int d = 1; d < G; d <<= 1) {
+            const double ob = __shfl_xor_sync(m, best, d, G); const int oi = __shfl_xor_sync(m, idx, d, G);
+            if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+        }
+#else
+        if (HostLaneTeam* t = host_lane_team())
+            for (int d = 1; d < G; d <<= 1) {
+                const double ob = t->shfl_f64(best, t->lane ^ d); const int oi = (int)t->shfl_u32((unsigned)idx, t->lane ^ d);
+                if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+            }
+#endif
+    }
     OD_HD static unsigned umax_all(unsigned v, unsigned m) {
 #ifdef __CUDA_ARCH__
 #pragma unroll

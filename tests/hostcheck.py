@@ -20,7 +20,7 @@ def build(flags=(), tag=""):
     srcs = [os.path.join(_HERE, "host_check.cu")] + [os.path.join(dp, f) for dp, _, fs in os.walk(csrc) for f in fs]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         os.makedirs(os.path.dirname(so), exist_ok=True)
-        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC", "-shared"] + list(flags) +
+        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-shared"] + list(flags) +
                               ["-o", so, os.path.join(_HERE, "host_check.cu")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     return so
 

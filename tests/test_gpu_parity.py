@@ -383,3 +383,67 @@ def test_sim_step_batch_matches_step_grad_batch(od):
     assert np.array_equal(g1, d1) and np.array_equal(g2, d2) and np.array_equal(gu, du)
     same = (stg == 0) & (st == 0)
     assert same.mean() > 0.98
+
+
+def test_user_model_on_the_gpu(od, tmp_path):
+    """SURVEY §8(f) N4 on hardware: a model that exists only as a specification file (tools/codegen/examples/particle_spec.py: point
+    mass, ground contact, Coulomb friction) is generated, compiled into its own library with the shipped solver templates
+    (user_model.build_user_model — no edit of the package's sources) and stepped on the GPU: closed-form free flight, stick / slip,
+    IFT sensitivities against central differences of the GPU step itself, and a random batch against the SAME generated header run
+    through the host-tier harness (tests/user_model_check.cu)."""
+    import ctypes as C
+    import subprocess
+    from optimization_dynamics_b200.user_model import build_user_model, UserModelDynamics, USER_DIR
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = build_user_model(os.path.join(root, "tools", "codegen", "examples", "particle_spec.py"))
+    m, g, h, mu = 1.5, 9.81, 0.05, 0.5
+    dyn = UserModelDynamics(so, h, κ_eval_tol=1e-6, κ_grad_tol=1e-6, friction=[mu])
+    assert (dyn.nq, dyn.nu) == (2, 2)
+    # free flight: q3 = 2 q2 − q1 + h² (u/m − g e_z)
+    q1 = np.array([[0.0, 1.0]]); q2 = np.array([[0.01, 1.02]]); u = np.array([[0.3, 0.2]])
+    q3, d1, d2, du, st = dyn.step_grad_batch(q1, q2, u)
+    assert st[0] == 0 and np.allclose(q3[0], 2 * q2[0] - q1[0] + h * h * (u[0] / m - np.array([0.0, g])), atol=1e-6)
+    # resting on the ground: a push inside the friction cone sticks, a large one slides with the kinetic-friction acceleration
+    z = np.zeros((1, 2))
+    q3, *_, st = dyn.step_grad_batch(z, z, np.array([[0.2 * m * g, 0.0]]))
+    assert st[0] == 0 and abs(q3[0, 1]) < 1e-5 and abs(q3[0, 0]) < 1e-5
+    q3, *_, st = dyn.step_grad_batch(z, z, np.array([[2.0 * m * g, 0.0]]))
+    assert st[0] == 0 and abs(q3[0, 1]) < 1e-5 and abs(q3[0, 0] - h * h * (2.0 - mu) * g) < 1e-5
+    # IFT sensitivities vs central differences (sliding contact: every block is exercised), all perturbed problems in ONE launch
+    tight = UserModelDynamics(so, h, κ_eval_tol=1e-9, κ_grad_tol=1e-9, friction=[mu])
+    base = np.array([0.0, 0.02, 0.01, 0.005, 1.0 * m * g, -2.0])
+    eps = 1e-6
+    rows = [base] + [base + s * eps * np.eye(6)[j] for j in range(6) for s in (1, -1)]
+    X = np.array(rows)
+    q3, d1, d2, du, st = tight.step_grad_batch(X[:, :2], X[:, 2:4], X[:, 4:])
+    assert (st == 0).all()
+    J = np.concatenate([d1[0], d2[0], du[0]], axis=1)
+    for j in range(6):
+        fd = (q3[1 + 2 * j] - q3[2 + 2 * j]) / (2 * eps)
+        assert np.allclose(J[:, j], fd, atol=2e-4), (j, J[:, j], fd)
+    # random batch (flight, resting, sliding) against the host-tier run of the same generated header
+    hdr = os.path.join(USER_DIR, "model_particle.cuh")
+    hso = str(tmp_path / "libusermodel_host.so")
+    subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-shared",
+                           "-DUSER_MODEL_HEADER=\"%s\"" % hdr, "-DUSER_MODEL=ParticleModel", "-o", hso, os.path.join(root, "tests", "user_model_check.cu")],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    H = C.CDLL(hso)
+    rng = np.random.default_rng(0)
+    B = 515
+    q2 = np.stack([rng.uniform(-1, 1, B), np.where(rng.uniform(size=B) < 0.5, 0.0, rng.uniform(0.0, 0.3, B))], axis=1)
+    v = rng.normal(0.0, 0.5, (B, 2)); v[q2[:, 1] == 0.0, 1] = 0.0
+    q1 = q2 - h * v
+    u = rng.normal(0.0, 5.0, (B, 2))
+    dyn = UserModelDynamics(so, h, κ_eval_tol=1e-4, κ_grad_tol=1e-3, friction=[mu])
+    q3, d1, d2, du, st = dyn.step_grad_batch(q1, q2, u)
+    hq3 = np.zeros((B, 2)); h1 = np.zeros((B, 2, 2)); h2 = np.zeros((B, 2, 2)); hu = np.zeros((B, 2, 2)); hst = np.zeros(B, dtype=np.int32)
+    dp = C.POINTER(C.c_double); p = lambda a: a.ctypes.data_as(dp)      # noqa: E731
+    fr = np.array([mu, 0, 0, 0.0])
+    assert H.um_step(B, p(np.ascontiguousarray(q1)), p(np.ascontiguousarray(q2)), p(np.ascontiguousarray(u)), C.c_double(h), p(fr), C.c_double(1e-4), C.c_double(1e-3),
+                     p(hq3), p(h1), p(h2), p(hu), hst.ctypes.data_as(C.POINTER(C.c_int)), 1) == 0
+    ok = (st == 0) & (hst == 0)
+    assert ok.mean() > 0.97 and np.array_equal(st == 0, hst == 0)
+    assert np.abs(q3 - hq3)[ok].max() <= Q3_TOL
+    eg = max(np.abs(d1 - h1.transpose(0, 2, 1))[ok].max(), np.abs(d2 - h2.transpose(0, 2, 1))[ok].max(), np.abs(du - hu.transpose(0, 2, 1))[ok].max())
+    print("user model on the GPU vs host tier: max|q3| %.2e  max|grad| %.2e  converged %.4f" % (np.abs(q3 - hq3)[ok].max(), eg, ok.mean()))
+    assert eg <= GRAD_TOL

@@ -354,7 +354,7 @@ def test_user_model_front_end(tmp_path):
                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     hdr = os.path.join(out, "model_particle.cuh")
     so = os.path.join(out, "libusermodel.so")
-    subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC", "-shared",
+    subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-shared",
                            "-DUSER_MODEL_HEADER=\"%s\"" % hdr, "-DUSER_MODEL=ParticleModel", "-o", so,
                            os.path.join(root, "tests", "user_model_check.cu")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     L = C.CDLL(so)
