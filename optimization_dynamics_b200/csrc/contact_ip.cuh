@@ -909,7 +909,20 @@ OD_HD bool warp_any(bool p) {
 #endif
 }
 
-template <class M, int G, int PPB, bool REG = false>
+// BSYNC (block-phased execution; large models): the warps of a block take the two votes of the state machine block-wide, through
+// __syncthreads_or — a barrier, so all warps of the block walk the loop in phase and every instruction-cache line that one warp
+// fetches serves the others (the planar push's loop is 108 KB of straight-line code: with 8 independent warps per SM every warp
+// streamed it from L2 on its own, 6 stall cycles per issued instruction).  A warp whose problems have all finished skips the body
+// and only keeps the barriers.
+OD_HD bool block_or(bool p) {
+#ifdef __CUDA_ARCH__
+    return __syncthreads_or(p) != 0;
+#else
+    return warp_any(p);
+#endif
+}
+
+template <class M, int G, int PPB, bool REG = false, bool BSYNC = false>
 OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const int g, const unsigned gmask) {
     typedef ContactIP<M, G, PPB, REG> IP;
     constexpr int NQ = M::NQ, NU = M::NU;
@@ -992,12 +1005,15 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
         if (active) {
             r_vio = rv2; k_vio = kv2;
 #else
-        IP::candidate(z, D, alpha, zc);
-        M::trig_var(zc.q, th, trv);
-        IP::residual(zc, th, trc, trv, rc, rv2, kv2);
-        const bool retry = active && !(first || rv2 <= r_vio || kv2 <= k_vio || ls >= a.opts.max_ls);
-        if (retry) { alpha *= a.opts.ls_scale; ++ls; }              // residual line search: halve and retry
-        if (warp_any(retry)) continue;                              // (the other problems of the warp re-evaluate their unchanged candidate)
+        bool retry = false;
+        if (!BSYNC || warp_any(active)) {                            // (BSYNC: a warp without live problems only keeps the barriers)
+            IP::candidate(z, D, alpha, zc);
+            M::trig_var(zc.q, th, trv);
+            IP::residual(zc, th, trc, trv, rc, rv2, kv2);
+            retry = active && !(first || rv2 <= r_vio || kv2 <= k_vio || ls >= a.opts.max_ls);
+            if (retry) { alpha *= a.opts.ls_scale; ++ls; }          // residual line search: halve and retry
+        }
+        if (BSYNC ? block_or(retry) : warp_any(retry)) continue;    // (the other problems of the warp / block re-evaluate their unchanged candidate)
         if (active) {
             z = zc; r_vio = rv2; k_vio = kv2;
 #endif
@@ -1026,7 +1042,8 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
             }
             if (bad || capped || (eval_done && grad_done)) active = false;
         }
-        if (!warp_any(active)) break;
+        if (BSYNC ? !block_or(active) : !warp_any(active)) break;
+        if constexpr (BSYNC) { if (!warp_any(active)) continue; }
         IP::linearize(z, th, trc, trv, rc, L);                   // trv still belongs to z (the candidate that was just accepted)
         if (active && !L.ok) {
             if (!eval_done) { st_e = ST_FAIL; it_e = it; eval_done = true; }
@@ -1170,14 +1187,15 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
 #ifndef OD_MIN_BLOCKS
 #define OD_MIN_BLOCKS 1
 #endif
-template <class M, int G, int PPB, bool REG>
+template <class M, int G, int PPB, bool REG, bool BSYNC = false>
 __global__ void __launch_bounds__(G * PPB, OD_MIN_BLOCKS) contact_step_kernel(const StepArgs a) {
     extern __shared__ __align__(16) double od_smem[];
     const int slot = threadIdx.x / G, g = threadIdx.x % G;
     static_assert((G * PPB) % 32 == 0, "whole warps: the step runs warp-synchronously");
     int i = blockIdx.x * PPB + slot;
     if (i >= a.B) i = a.B - 1;               // padding lanes of the last warp repeat the last problem (identical values, same addresses)
-    contact_step_one<M, G, PPB, REG>(a, i, od_smem + slot * ContactIP<M, G, PPB, REG>::WS_SLOT, g, 0xffffffffu);
+    static_assert(!BSYNC || !OD_INPLACE_Z, "block-phased execution is written for the two-copy iterate update");
+    contact_step_one<M, G, PPB, REG, BSYNC>(a, i, od_smem + slot * ContactIP<M, G, PPB, REG>::WS_SLOT, g, 0xffffffffu);
     if (a.sync_counter) {                                   // fused cross-GPU barrier (see StepArgs)
         // The block barrier orders every thread's peer / multicast stores before thread 0's system-scope fence, which is cumulative
         // (the pattern of cooperative-groups grid sync: bar.sync, then ONE thread fences and signals) — one fence per block, not per thread.

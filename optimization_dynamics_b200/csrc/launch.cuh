@@ -8,16 +8,23 @@
 
 namespace od {
 
-template <class M, int G, int PPB, bool REG>
+template <class M, int G, int PPB, bool REG, bool BSYNC = false>
 static inline cudaError_t launch_contact_cfg(const StepArgs& a, cudaStream_t s) {
     const int grid = (a.B + PPB - 1) / PPB;
     constexpr size_t smem = sizeof(double) * PPB * ContactIP<M, G, PPB, REG>::WS;
     if (smem > 48 * 1024) {   // > 48 KB of dynamic shared memory needs an explicit opt-in; per device, so set at every launch
-        cudaError_t e = cudaFuncSetAttribute(contact_step_kernel<M, G, PPB, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(contact_step_kernel<M, G, PPB, REG, BSYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    contact_step_kernel<M, G, PPB, REG><<<grid, G * PPB, smem, s>>>(a);
+    contact_step_kernel<M, G, PPB, REG, BSYNC><<<grid, G * PPB, smem, s>>>(a);
     return cudaGetLastError();
+}
+// OD_BSYNC (default 1): block-phased execution for the models whose loop does not fit the instruction caches (planar push), from
+// this batch size on — below it the batch cannot fill the machine with 256-thread blocks and 16 lanes per problem win on latency.
+inline int bsync_min_batch() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("OD_BSYNC"); v = e ? atoi(e) : 1; if (v == 1) v = 4097; }
+    return v;      // 0 = never, 1 = default threshold, n > 1 = from n problems on
 }
 
 // Lanes per problem: 1 = one thread per problem (throughput configuration, large batches; LU in shared memory); 4 / 8 =
@@ -45,6 +52,10 @@ static inline cudaError_t launch_contact(const StepArgs& a, cudaStream_t s) {
     const int lanes = lanes_for(a.B, M::ROBUST_IFT);
     if constexpr (REGOK) {
         if (reg_path()) {
+            if constexpr (WIDE && M::ROBUST_IFT) {
+                // a gather with peers keeps one-warp blocks (the fused barrier counts blocks as they finish; rows should leave early)
+                if (bsync_min_batch() > 0 && a.B >= bsync_min_batch() && lanes == 8 && a.n_peers <= 1) return launch_contact_cfg<M, 8, 32, true, true>(a, s);
+            }
             if constexpr (WIDE) { if (lanes == 16) return launch_contact_cfg<M, 16, 2, true>(a, s); }
             if constexpr (WIDE) { if (lanes == 8) return launch_contact_cfg<M, 8, 4, true>(a, s); }
             if (lanes >= 4) return launch_contact_cfg<M, 4, 8, true>(a, s);

@@ -19,27 +19,36 @@ namespace od {
 // The cost is quadratic, so the reference's Newton loop converges in one step to the normal-equation solution
 // M = (Σ (fη_k − fz) η_kᵀ)(Σ η_k η_kᵀ)⁻¹; the second factor depends only on the shared perturbations and is inverted once.
 // ---------------------------------------------------------------------------------------------------------------------
+// One block per problem, one thread per (output component i, coordinate l): G[l][i] = Σ_k (fη_k − fz)_i η_k[l] in sample order, then
+// M[i][j] = Σ_l G[l][i] Hinv[l][j] (the first version ran the whole fit of a problem on one thread: 81 µs for the 50-problem sweep of
+// BASELINE configs[1], five times the solves it follows).
 __global__ void bundle_fit_kernel(int B, int N, int nq, int ncol, const double* __restrict__ feta /*B×(N+1)×nq*/, const double* __restrict__ eta /*N×ncol*/,
                                   const double* __restrict__ Hinv /*ncol×ncol*/, const int* __restrict__ st_in /*B×(N+1)*/, double* __restrict__ dz, int* __restrict__ st_out) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double G[16 * 16];
+    __shared__ int st_sh;
+    const int b = blockIdx.x, t = threadIdx.x;
     if (b >= B) return;
+    if (t == 0) st_sh = 0;
+    __syncthreads();
     const double* f = feta + (size_t)b * (N + 1) * nq;
-    int st = st_in[(size_t)b * (N + 1)];
-    for (int k = 0; k < N; ++k) st |= st_in[(size_t)b * (N + 1) + 1 + k];
-    for (int i = 0; i < nq; ++i) {
-        double G[16];   // ncol ≤ 16
-        for (int j = 0; j < ncol; ++j) G[j] = 0.0;
-        for (int k = 0; k < N; ++k) {
-            const double df = f[(size_t)(k + 1) * nq + i] - f[i];
-            for (int j = 0; j < ncol; ++j) G[j] += df * eta[(size_t)k * ncol + j];
-        }
-        for (int j = 0; j < ncol; ++j) {
-            double m = 0.0;
-            for (int l = 0; l < ncol; ++l) m += G[l] * Hinv[l * ncol + j];
-            dz[(size_t)b * nq * ncol + (size_t)j * nq + i] = m;
-        }
+    int st = 0;
+    for (int k = t; k <= N; k += blockDim.x) st |= st_in[(size_t)b * (N + 1) + k];
+    if (st) atomicOr(&st_sh, st);
+    const int i = t % nq, l = t / nq;
+    if (l < ncol) {
+        double g = 0.0;
+        const double fz = f[i];
+        for (int k = 0; k < N; ++k) g += (f[(size_t)(k + 1) * nq + i] - fz) * eta[(size_t)k * ncol + l];
+        G[l * nq + i] = g;
     }
-    if (st_out) st_out[b] = st;
+    __syncthreads();
+    if (l < ncol) {
+        const int j = l;
+        double m = 0.0;
+        for (int ll = 0; ll < ncol; ++ll) m += G[ll * nq + i] * Hinv[ll * ncol + j];
+        dz[(size_t)b * nq * ncol + (size_t)j * nq + i] = m;
+    }
+    if (t == 0 && st_out) st_out[b] = st_sh;
 }
 
 }  // namespace od
@@ -625,7 +634,7 @@ int od_bundle_fit_device(od_handle* hd, int B, int N, const double* eta, const d
     if (B <= 0) return 0;
     if (N <= 0 || !eta || !Hinv || !feta || !st_work || !dz) return fail("od_bundle_fit_device: bad arguments");
     OD_CUDA(cudaSetDevice(hd->device));
-    bundle_fit_kernel<<<(B + 63) / 64, 64, 0, hd->stream>>>(B, N, d.nq, 2 * d.nq + d.nu, feta, eta, Hinv, st_work, dz, status);
+    bundle_fit_kernel<<<B, ((d.nq * (2 * d.nq + d.nu) + 31) / 32) * 32, 0, hd->stream>>>(B, N, d.nq, 2 * d.nq + d.nu, feta, eta, Hinv, st_work, dz, status);
     OD_CUDA(cudaGetLastError());
     hd->launches++;
     return 0;
