@@ -409,6 +409,63 @@ class Sweep:
             self.info.step_batch(self.e_np[0], self.e_np[1], proj=True)
 
 
+def single_call_latency(sw, reps=200):
+    """BASELINE configs[0] is ONE rollout on the CPU: the reference's outer solver calls f / fx / fu once per timestep
+    (examples/acrobot.jl:92,113).  Latency of exactly those calls through the host API (one problem per call = launch + synchronise)
+    next to the CPU restatement on one thread, and the whole T-step rollout as one launch (od_rollout_batch) next to T−1 sequential f calls."""
+    import numpy as np
+    od, cfg = sw.od, sw.cfg
+    from oracle import oracle as O
+    name = ORACLE_NAME[cfg["model"]]
+    nq, nu = sw.dyn.nq, sw.dyn.nu
+    row = sw.x_host_full[0]
+    x = np.ascontiguousarray(row[:2 * nq]); u0 = np.ascontiguousarray(row[2 * nq:]); w = np.zeros(0)
+    d = np.zeros(2 * nq); dx = np.zeros((2 * nq, 2 * nq)); du = np.zeros((2 * nq, nu))
+    us = [u0 + 1e-9 * k for k in range(reps)]                      # a new control every call: no memoised gradient
+    for k in range(5):
+        od.f(d, sw.dyn, x, us[k], w); od.fx(dx, sw.dyn, x, us[k], w); od.fu(du, sw.dyn, x, us[k], w)
+    t0 = time.perf_counter()
+    for k in range(reps):
+        od.f(d, sw.dyn, x, us[k], w)
+    t_f = (time.perf_counter() - t0) / reps
+    t0 = time.perf_counter()
+    for k in range(reps):
+        od.fx(dx, sw.dyn, x, us[k], w); od.fu(du, sw.dyn, x, us[k], w)
+    t_g = (time.perf_counter() - t0) / reps
+    q1, q2 = x[None, :nq], x[None, nq:]
+    t0 = time.perf_counter()
+    for k in range(reps):
+        O.step_batch(name, q1, q2, us[k][None], cfg["h"], cfg["ke"], False, fric=cfg["fric"], r_tol=R_TOL, nthreads=1, diagnostics=False)
+    c_f = (time.perf_counter() - t0) / reps
+    t0 = time.perf_counter()
+    for k in range(reps):
+        O.step_batch(name, q1, q2, us[k][None], cfg["h"], cfg["kg"], True, fric=cfg["fric"], r_tol=R_TOL, nthreads=1, diagnostics=False)   # fx
+        O.step_batch(name, q1, q2, us[k][None], cfg["h"], cfg["kg"], True, fric=cfg["fric"], r_tol=R_TOL, nthreads=1, diagnostics=False)   # fu re-solves
+    c_g = (time.perf_counter() - t0) / reps
+    T = 51
+    ubar = np.tile(u0, (T - 1, 1)) * 0.1
+    od.rollout(sw.dyn, x, ubar)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        od.rollout(sw.dyn, x, ubar)
+    t_roll = (time.perf_counter() - t0) / 20
+    t0 = time.perf_counter()
+    for _ in range(5):
+        xx = x.copy()
+        for t in range(T - 1):
+            od.f(d, sw.dyn, xx, ubar[t], w); xx = d.copy()
+    t_seq = (time.perf_counter() - t0) / 5
+    t0 = time.perf_counter()
+    for _ in range(5):
+        O.rollout_batch(name, x[None], ubar, cfg["h"], cfg["ke"], fric=cfg["fric"], r_tol=R_TOL)
+    c_roll = (time.perf_counter() - t0) / 5
+    return {"unit": "us per call", "f_gpu_host_api": 1e6 * t_f, "fx_plus_fu_gpu_host_api": 1e6 * t_g, "f_cpu_oracle_1_thread": 1e6 * c_f,
+            "fx_plus_fu_cpu_oracle_1_thread_reference_pattern": 1e6 * c_g,
+            "rollout_T51_one_launch_us": 1e6 * t_roll, "rollout_T51_as_50_sequential_f_calls_us": 1e6 * t_seq, "rollout_T51_cpu_oracle_us": 1e6 * c_roll,
+            "note": "one problem per call = one kernel launch + synchronise: the GPU loses to one CPU core on a single tiny solve; the batched entry points "
+                    "(all timesteps of the sweep, all line-search candidates of the forward pass) are what the device path is for"}
+
+
 def timed_region(sweep, steps, barrier, use_graph):
     """K steps between two CUDA events, barrier + synchronize on both sides.  Returns (milliseconds, 'graph' | 'eager')."""
     torch = sweep.torch
@@ -591,6 +648,8 @@ def main():
             "gpu_launches": int(main_res["launches"]) * world,
             "clocks": main_res["clk"],
         }
+        if name == "acrobot" and world == 1 and not args.no_cpu_baseline:
+            extra["single_call_latency"] = single_call_latency(sw)
         if extra:
             line["extra"] = extra
         if not args.no_cpu_baseline:

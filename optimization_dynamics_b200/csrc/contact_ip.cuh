@@ -21,11 +21,23 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdint.h>
 #include "group_gj.cuh"
 
 // 1: the pivot row of every elimination step travels through the shared-memory staging area (GroupGJ::factor_sm), 0: by shuffles.
 #ifndef OD_GJ_SMEM
 #define OD_GJ_SMEM 1
+#endif
+// 1 (experiment, off): the block's input rows are staged by one cp.async.bulk (TMA) copy, see contact_step_kernel
+#ifndef OD_TMA_INPUT
+#define OD_TMA_INPUT 0
+#endif
+// Reduced systems of this size and larger are factorised in shared memory with rolled loops (ContactIP::LASM, GroupGJS).  OFF in the
+// shipped build (99): measured on B200 (profiles/r02h_*), the rolled shared-memory elimination removes the instruction-cache stalls
+// and the spills but pays for it in shared-memory latency on the dependent LDS → FMA → STS chain (short-scoreboard stalls 1.0 → 2.5
+// per issue, half the wavefronts bank-conflicted): hopper 4096 0.064 → 0.107 ms, planar push 25 600 6.5 → 10.3 ms.
+#ifndef OD_LA_SMEM_MIN_NR
+#define OD_LA_SMEM_MIN_NR 99
 #endif
 // 1 (prepared, off): iterate advanced in place, see contact_step_one
 #ifndef OD_INPLACE_Z
@@ -124,7 +136,11 @@ struct ContactIP {
     static constexpr int ROBUST_END = M::ROBUST_IFT ? OFF_CP + NR : 0;
     static constexpr int ROFF_ZS = ((((NR * PW > ROBUST_END) ? NR * PW : ROBUST_END) + 1) / 2) * 2;
     static constexpr int ROFF_Q3 = ROFF_ZS + NZ;
-    static constexpr int RWS0 = ((ROFF_Q3 + NQ + 1) / 2) * 2;
+    // LASM (A/B switch, off by default — see OD_LA_SMEM_MIN_NR): the Newton systems are factorised in place in the staging area
+    // with rolled loops (GroupGJS) instead of in registers; -DOD_LA_SMEM_MIN_NR=1 builds every model that way.
+    static constexpr bool LASM = REG && (NR >= OD_LA_SMEM_MIN_NR) && (PW >= NR + 1 + ((NR + 1) % 2) + 2);
+    static constexpr int ROFF_PV = ((ROFF_Q3 + NQ + 1) / 2) * 2;          // pivot rows of the elimination steps (ints)
+    static constexpr int RWS0 = ROFF_PV + (LASM ? ((NR + 3) / 4) * 2 : 0);
     static constexpr int RWS = ((RWS0 / 2) % 2 == 1) ? RWS0 : RWS0 + 2;
     static constexpr int NOUT = NQ + NQ * NTP;           // packed output row [q3 | ∂q3/∂q1 | ∂q3/∂q2 | ∂q3/∂u1]
     static_assert(!REG || NOUT <= NR * PW, "output row is staged in the matrix area");
@@ -132,6 +148,7 @@ struct ContactIP {
     static constexpr int WS_STRIDE = REG ? 1 : PPB;      // distance between consecutive elements of one problem
     static constexpr int WS_SLOT = REG ? RWS : 1;        // distance between the workspaces of consecutive problems of a block
     typedef GroupGJ<NR, NR + 1, G> GJ;                   // Newton systems: one carried right-hand side (the affine one)
+    typedef GroupGJS<NR, NR + 1, G, PW> GJSM;            // the same, matrix resident in shared memory (LASM)
     typedef GroupGJ<NR, NR + NTP, G> GJS;                // sensitivity system: all NTP right-hand sides carried
     static constexpr int RPL = GJ::RPL;
 
@@ -144,8 +161,9 @@ struct ContactIP {
         int g;                       // lane within the group
         unsigned gmask;              // shuffle / __syncwarp mask (the whole warp: execution is warp-synchronous)
         bool ok;
-        double a[REG ? RPL : 1][REG ? NR + 1 : 1];   // REG: this lane's rows of the eliminated [K | affine rhs]
-        int piv[REG ? NR : 1];                       // REG: pivot row of every elimination step
+        double a[(REG && !LASM) ? RPL : 1][(REG && !LASM) ? NR + 1 : 1];   // REG: this lane's rows of the eliminated [K | affine rhs]
+        int piv[(REG && !LASM) ? NR : 1];                                  // REG: pivot row of every elimination step
+        OD_HD int* PV() const { return reinterpret_cast<int*>(ws + ROFF_PV); }   // LASM: the same, in the workspace
         OD_HD double& S(int r, int j) const { return ws[r * PW + j]; }     // REG staging area
         OD_HD double& K(int i, int j) const { return ws[(i * NRP + j) * WS_STRIDE]; }
         OD_HD double& X(int v, int i) const { return ws[(OFF_X + v * NRP + i) * WS_STRIDE]; }
@@ -208,15 +226,19 @@ struct ContactIP {
 #pragma unroll
             for (int i = 0; i < NR; ++i) L.S(i, NR) = x[i];
             L.sync();
-            fetch_rows<NR + 1>(L, L.a);
+            if constexpr (LASM) {
+                L.ok = GJSM::factor(&L.S(0, 0), L.PV(), L.g, L.gmask);
+            } else {
+                fetch_rows<NR + 1>(L, L.a);
 #if OD_GJ_SMEM && OD_EXTRACT_SMEM
-            if constexpr (PW >= GJ::CINV + 2) L.ok = GJ::template factor_v2<PW>(L.a, L.piv, L.g, L.gmask, &L.S(0, 0));
-            else L.ok = GJ::template factor_sm<PW>(L.a, L.piv, L.g, L.gmask, &L.S(0, 0));
+                if constexpr (PW >= GJ::CINV + 2) L.ok = GJ::template factor_v2<PW>(L.a, L.piv, L.g, L.gmask, &L.S(0, 0));
+                else L.ok = GJ::template factor_sm<PW>(L.a, L.piv, L.g, L.gmask, &L.S(0, 0));
 #elif OD_GJ_SMEM
-            L.ok = GJ::template factor_sm<PW>(L.a, L.piv, L.g, L.gmask, &L.S(0, 0));
+                L.ok = GJ::template factor_sm<PW>(L.a, L.piv, L.g, L.gmask, &L.S(0, 0));
 #else
-            L.ok = GJ::factor(L.a, L.piv, L.g, L.gmask);
+                L.ok = GJ::factor(L.a, L.piv, L.g, L.gmask);
 #endif
+            }
         } else {
             assemble(z, th, trc, trv, L); factor(L);
         }
@@ -450,7 +472,11 @@ struct ContactIP {
     OD_HD static void solve(const Lin& L, const Z& z, const R& r, Z& D) {
         double x[NR];
         load_rhs(z, r, x);
-        if constexpr (REG) {
+        if constexpr (LASM) {
+            double xm[RPL];
+            GJ::mine(x, xm, L.g);
+            GJSM::solve(&L.S(0, 0), L.PV(), xm, x, L.g, L.gmask);
+        } else if constexpr (REG) {
             double xm[RPL];
             GJ::mine(x, xm, L.g);
 #if OD_EXTRACT_SMEM && OD_GJ_SMEM
@@ -466,7 +492,11 @@ struct ContactIP {
     }
     // REG: direction for the right-hand side that linearize() carried through the elimination (the residual at z itself)
     OD_HD static void solve_carried(const Lin& L, const Z& z, const R& r, Z& D) {
-        if constexpr (REG) {
+        if constexpr (LASM) {
+            double x[NR];
+            GJSM::extract(&L.S(0, 0), L.PV(), 0, x);
+            expand(L, r, x, D);
+        } else if constexpr (REG) {
             double x[NR];
 #if OD_EXTRACT_SMEM && OD_GJ_SMEM
             if constexpr (PW >= GJ::CINV + 2) GJ::template extract_sm<PW>(L.a, L.piv, 0, x, L.g, L.gmask, &L.S(0, 0));
@@ -1195,6 +1225,36 @@ __global__ void __launch_bounds__(G * PPB, OD_MIN_BLOCKS) contact_step_kernel(co
     int i = blockIdx.x * PPB + slot;
     if (i >= a.B) i = a.B - 1;               // padding lanes of the last warp repeat the last problem (identical values, same addresses)
     static_assert(!BSYNC || !OD_INPLACE_Z, "block-phased execution is written for the two-copy iterate update");
+#if OD_TMA_INPUT
+    // Experiment for the north_star's "TMA staging" clause (A/B switch, off in the shipped build): the block's packed
+    // input rows (PPB × 80 B for the hopper) arrive in shared memory as ONE bulk asynchronous copy (cp.async.bulk, the 1-D TMA path,
+    // completion on an mbarrier) instead of per-lane global loads; the solver then reads its row from shared memory.
+    if (a.in_packed && !a.eta && (reinterpret_cast<uintptr_t>(a.q1) & 15) == 0) {
+        constexpr int NIN = 2 * M::NQ + M::NU;
+        static_assert((NIN * 8 * PPB) % 16 == 0, "bulk copies move multiples of 16 bytes");
+        __shared__ __align__(16) double tile[PPB * NIN];
+        __shared__ __align__(8) unsigned long long mbar;
+        const int row0 = blockIdx.x * PPB;
+        const int rows = (a.B - row0 < PPB) ? a.B - row0 : PPB;
+        const unsigned bytes = (unsigned)(rows * NIN * 8);
+        const unsigned mb = (unsigned)__cvta_generic_to_shared(&mbar), dst = (unsigned)__cvta_generic_to_shared(tile);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(a.q1 + (size_t)row0 * NIN), "r"(bytes), "r"(mb) : "memory");
+        }
+        unsigned done = 0;
+        while (!done) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb) : "memory");
+        StepArgs b = a;
+        b.q1 = tile - (size_t)row0 * NIN; b.q2 = b.q1 + M::NQ; b.u = b.q1 + 2 * M::NQ;       // row i of the batch = row i − row0 of the tile
+        contact_step_one<M, G, PPB, REG, BSYNC>(b, i, od_smem + slot * ContactIP<M, G, PPB, REG>::WS_SLOT, g, 0xffffffffu);
+    } else
+#endif
     contact_step_one<M, G, PPB, REG, BSYNC>(a, i, od_smem + slot * ContactIP<M, G, PPB, REG>::WS_SLOT, g, 0xffffffffu);
     if (a.sync_counter) {                                   // fused cross-GPU barrier (see StepArgs)
         // The block barrier orders every thread's peer / multicast stores before thread 0's system-scope fence, which is cumulative

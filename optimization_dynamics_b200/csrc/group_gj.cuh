@@ -394,4 +394,126 @@ struct GroupGJ {
     }
 };
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same elimination with the matrix RESIDENT in shared memory and every loop over elimination steps rolled.
+//
+// Why: the register-resident GroupGJ needs compile-time column indices, so its NR steps are NR copies of the code — 1.9 k
+// instructions for the planar push's 20×21 system, 0.9 k for the hopper's 12×13 — and the interior-point loop around it no longer
+// fits the 32 KB instruction cache: ncu shows 6.0 (planar push), 3.3 (rocket) and 0.8 (hopper) stall cycles per issued instruction
+// waiting for instructions.  Here row r still belongs to lane r mod G (only its owner writes it; everybody reads the pivot row), the
+// step loop is one copy of the code with run-time addresses, pairs of columns move as 16-byte words, and the per-lane register
+// image of the matrix (RPL·NCOL doubles) is gone.  Same arithmetic in the same order as GroupGJ::factor_v2 / solve_sm / extract_sm
+// (bit-identical results; tests/test_host_logic.py holds the two against each other).
+// S: row r at S + r·PITCH (PITCH even, ≥ CINV + 2: inverse pivots in column CINV, scaled solution in CSOL); PV: NR ints in shared memory.
+template <int NR, int NCOL, int G, int PITCH>
+struct GroupGJS {
+    static constexpr int RPL = (NR + G - 1) / G;
+    static constexpr int LG = Grp<G>::LG;
+    static constexpr int CINV = NCOL + (NCOL % 2), CSOL = CINV + 1;
+    static_assert(RPL * G <= 32 && NCOL >= NR && PITCH % 2 == 0 && PITCH >= CINV + 2, "layout");
+    OD_HD static void sync(const unsigned gm) {
+#ifdef __CUDA_ARCH__
+        if (G > 1) __syncwarp(gm);
+#else
+        if (G > 1) host_team_sync();
+#endif
+    }
+    OD_HD static bool factor(double* S, int* PV, const int g, const unsigned gm) {
+        bool ok = true;
+        bool cand[RPL];
+#pragma unroll
+        for (int s = 0; s < RPL; ++s) cand[s] = (s * G + g < NR);
+#pragma unroll 1
+        for (int k = 0; k < NR; ++k) {
+            if (k > 0) sync(gm);                                   // the rows as updated by step k − 1
+            unsigned key = 0;
+            double best = (G <= NR || g < NR) ? S[g * PITCH + k] : 0.0;
+#pragma unroll
+            for (int s = 0; s < RPL; ++s) {
+                const int r = s * G + g;
+                const bool in = (G == 1) || ((s + 1) * G <= NR) || (r < NR);
+                const double v = in ? S[r * PITCH + k] : 0.0;
+                const unsigned ks = cand[s] ? ((abs_hi32(v) & ~31u) | (unsigned)r) : 0u;
+                if (s > 0) best = (ks > key) ? v : best;
+                key = ks > key ? ks : key;
+            }
+            const double myinv = pivot_rcp(best);
+            key = Grp<G>::umax_all(key, gm);
+            ok = ok && (key >= 32u) && (key < 0x7ff00000u);
+            const int pr = (int)(key & 31u);
+            PV[k] = pr;                                            // every lane stores the same value
+            const double inv = Grp<G>::bcast(myinv, pr & (G - 1), gm);
+            const double* prow = S + pr * PITCH;
+            S[pr * PITCH + CINV] = inv;
+            double me[RPL]; bool upd[RPL];
+#pragma unroll
+            for (int s = 0; s < RPL; ++s) {
+                const int r = s * G + g;
+                const bool in = (G == 1) || ((s + 1) * G <= NR) || (r < NR);
+                const bool isp = (pr == r);
+                cand[s] = cand[s] && !isp;
+                const double m = (in ? S[r * PITCH + k] : 0.0) * inv;
+                me[s] = isp ? 0.0 : m;
+                upd[s] = in && !isp;                               // the pivot row itself stays as it is (a − 0·a)
+                if (in) S[r * PITCH + k] = me[s];
+            }
+            int j = k + 1;
+            if (j & 1) {
+                if (j < NCOL) {
+                    const double pv = prow[j];
+#pragma unroll
+                    for (int s = 0; s < RPL; ++s) if (upd[s]) S[(s * G + g) * PITCH + j] -= me[s] * pv;
+                }
+                ++j;
+            }
+#pragma unroll 2
+            for (; j < NCOL; j += 2) {                             // (an odd NCOL drags its pad column along: never read back)
+                const double2 pv = *reinterpret_cast<const double2*>(prow + j);
+#pragma unroll
+                for (int s = 0; s < RPL; ++s) {
+                    if (upd[s]) {
+                        double2* p = reinterpret_cast<double2*>(S + (s * G + g) * PITCH + j);
+                        double2 o = *p;
+                        o.x -= me[s] * pv.x; o.y -= me[s] * pv.y;
+                        *p = o;
+                    }
+                }
+            }
+        }
+        sync(gm);
+        return ok;
+    }
+    // solution of the carried right-hand side in column NR + c, replicated in every lane (sol[k]: compile-time indices)
+    OD_HD static void extract(const double* S, const int* PV, const int c, double* sol) {
+#pragma unroll
+        for (int k = 0; k < NR; ++k) { const double* row = S + PV[k] * PITCH; sol[k] = row[NR + c] * row[CINV]; }
+    }
+    // a further right-hand side (x = this lane's rows of it) through the stored multipliers; solution replicated in every lane
+    OD_HD static void solve(double* S, const int* PV, double (&x)[RPL], double* sol, const int g, const unsigned gm) {
+#pragma unroll 1
+        for (int k = 0; k < NR; ++k) {
+            const int pr = PV[k], wl = pr & (G - 1), ws = pr >> LG;
+            double xs = x[0];
+#pragma unroll
+            for (int t = 1; t < RPL; ++t) xs = (ws == t) ? x[t] : xs;
+            const double xp = Grp<G>::bcast(xs, wl, gm);
+#pragma unroll
+            for (int s = 0; s < RPL; ++s) {
+                const int r = s * G + g;
+                const bool in = (G == 1) || ((s + 1) * G <= NR) || (r < NR);
+                x[s] -= (in ? S[r * PITCH + k] : 0.0) * xp;        // the pivot row of step k holds a zero in column k
+            }
+        }
+        sync(gm);                                                  // earlier readers of column CSOL are done
+#pragma unroll
+        for (int s = 0; s < RPL; ++s) {
+            const int r = s * G + g;
+            if (G == 1 || (s + 1) * G <= NR || r < NR) S[r * PITCH + CSOL] = x[s] * S[r * PITCH + CINV];
+        }
+        sync(gm);
+#pragma unroll
+        for (int k = 0; k < NR; ++k) sol[k] = S[PV[k] * PITCH + CSOL];
+    }
+};
+
 }  // namespace od

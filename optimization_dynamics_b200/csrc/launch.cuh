@@ -19,12 +19,15 @@ static inline cudaError_t launch_contact_cfg(const StepArgs& a, cudaStream_t s) 
     contact_step_kernel<M, G, PPB, REG, BSYNC><<<grid, G * PPB, smem, s>>>(a);
     return cudaGetLastError();
 }
-// OD_BSYNC (default 1): block-phased execution for the models whose loop does not fit the instruction caches (planar push), from
-// this batch size on — below it the batch cannot fill the machine with 256-thread blocks and 16 lanes per problem win on latency.
+// OD_BSYNC (default 0 = off): block-phased execution for the models whose loop does not fit the instruction caches (planar push).
+// Measured on B200 (profiles/r02g_*, 25 600 problems): the barrier-aligned warps do share their instruction fetches (stall cycles per
+// issue waiting for instructions 5.97 → 0.15), but a 256-thread block lasts as long as the slowest of its 32 problems and holds its
+// SM while the finished warps wait at the barrier (5.2 barrier-stall cycles per issue): 6.53 → 6.62 ms, no gain.  OD_BSYNC=1 turns it
+// on from 4097 problems, OD_BSYNC=n from n problems.
 inline int bsync_min_batch() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("OD_BSYNC"); v = e ? atoi(e) : 1; if (v == 1) v = 4097; }
-    return v;      // 0 = never, 1 = default threshold, n > 1 = from n problems on
+    if (v < 0) { const char* e = getenv("OD_BSYNC"); v = e ? atoi(e) : 0; if (v == 1) v = 4097; }
+    return v;
 }
 
 // Lanes per problem: 1 = one thread per problem (throughput configuration, large batches; LU in shared memory); 4 / 8 =

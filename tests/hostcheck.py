@@ -13,8 +13,12 @@ DIMS = {"acrobot_impact": (2, 1), "acrobot_nominal": (2, 1), "cartpole_friction"
         "planar_push": (5, 2), "hopper": (4, 2)}
 
 
-def build(flags=(), tag=""):
-    """flags: extra -D… switches of the kernels' prepared variants (built as a separate library, tag = its file-name suffix)."""
+def build(flags=None, tag=""):
+    """flags: the -D… switches of the build (None = the shipped library's, _lib.DEFAULT_DEFINES; a variant is built as a separate
+    library, tag = its file-name suffix)."""
+    if flags is None:
+        from optimization_dynamics_b200 import _lib
+        flags = _lib.DEFAULT_DEFINES
     so = os.path.join(_HERE, "_build", "libhostcheck%s.so" % tag)
     csrc = os.path.join(_ROOT, "optimization_dynamics_b200", "csrc")
     srcs = [os.path.join(_HERE, "host_check.cu")] + [os.path.join(dp, f) for dp, _, fs in os.walk(csrc) for f in fs]

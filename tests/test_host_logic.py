@@ -293,6 +293,26 @@ def test_prepared_mirror_variant_matches_shipped_path(name, lanes, B, flags, tag
                 assert np.allclose(base[k], other[k], rtol=0, atol=1e-9, equal_nan=True), k
 
 
+@pytest.mark.parametrize("name,lanes,B", [("hopper", 8, 22), ("hopper", 4, 13), ("hopper", 16, 5), ("cartpole_friction", 4, 19),
+                                          ("acrobot_impact", 4, 11), ("planar_push", 16, 4), ("planar_push", 8, 6), ("planar_push", 4, 5)])
+def test_shared_memory_resident_elimination_matches_register_path(name, lanes, B):
+    """GroupGJS (matrix resident in shared memory, rolled step loop — an A/B option, ContactIP::LASM; measured slower, off) against the
+    register-resident GroupGJ: same arithmetic in the same order, so bit-identical, with one lane and with cooperative lanes.
+    -DOD_LA_SMEM_MIN_NR=1 builds every model on GroupGJS, -DOD_LA_SMEM_MIN_NR=99 none."""
+    gen, h, ke, kg, fric, _ = CONFIGS[name]
+    q1, q2, u = gen(B, h=h, seed=13)
+    with H.use_variant(["-DOD_EXTRACT_SMEM=1", "-DOD_LA_SMEM_MIN_NR=99"], "_lareg"):
+        base = H.step(name, q1, q2, u, h, ke, kg, fric=fric, reg=lanes)
+    with H.use_variant(["-DOD_EXTRACT_SMEM=1", "-DOD_LA_SMEM_MIN_NR=1"], "_lasm"):
+        var1 = H.step(name, q1, q2, u, h, ke, kg, fric=fric, reg=1)
+        var = H.step(name, q1, q2, u, h, ke, kg, fric=fric, reg=lanes)
+    assert (base["status"] == 0).mean() > 0.7
+    for other in (var1, var):
+        assert np.array_equal(base["status"], other["status"]) and np.array_equal(base["it_eval"], other["it_eval"])
+        for k in ("q3", "dq1", "dq2", "du"):
+            assert np.array_equal(base[k], other[k], equal_nan=True), k
+
+
 @pytest.mark.parametrize("variant", [None, "-DOD_EXTRACT_SMEM=1"])       # (OD_INPLACE_Z only touches the contact state machine)
 def test_cooperative_lanes_rocket_and_rollouts_on_the_host(variant):
     """rocket_kernel_g (dense 12×12 dynamics + 10×10 cone projection + chain rule) and the closed-loop rollout template with

@@ -36,20 +36,29 @@ __global__ void __launch_bounds__(32) update_kernel(const double* __restrict__ i
             // panel p = matrix columns / rows 4p … 4p+3: tile column jp = p/2 (columns (p%2)*4 … +3 of it), tile row ip = p/2
             const int jp = p / 2, ip = p / 2, off = (p % 2) * 4;
             if (VARIANT == 0) {
+                // L (24×4) and U (4×32) are read BEFORE the update, as in a blocked elimination (the panel is final when the
+                // trailing update starts): both variants compute C − L·U with the same operands
+                double l[4][MT], u[4][NT][2];
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
                     const int col = off + kk;                    // column inside tile jp: owner quad = col/2, element col%2
-                    double l[MT];
 #pragma unroll
-                    for (int i = 0; i < MT; ++i) l[i] = 0.015625 * __shfl_sync(0xffffffffu, c[i][jp][col & 1], (lane & ~3) | (col >> 1));
+                    for (int i = 0; i < MT; ++i) {
+                        const double v0 = __shfl_sync(0xffffffffu, c[i][jp][0], (lane & ~3) | (col >> 1)), v1 = __shfl_sync(0xffffffffu, c[i][jp][1], (lane & ~3) | (col >> 1));
+                        l[kk][i] = 0.015625 * ((col & 1) ? v1 : v0);
+                    }
                     const int urow = off + kk;                   // row inside tile row ip: owner lanes urow*4 + quad
 #pragma unroll
                     for (int j = 0; j < NT; ++j) {
-                        const double u0 = __shfl_sync(0xffffffffu, c[ip][j][0], urow * 4 + quad), u1 = __shfl_sync(0xffffffffu, c[ip][j][1], urow * 4 + quad);
-#pragma unroll
-                        for (int i = 0; i < MT; ++i) { c[i][j][0] = fma(-l[i], u0, c[i][j][0]); c[i][j][1] = fma(-l[i], u1, c[i][j][1]); }
+                        u[kk][j][0] = __shfl_sync(0xffffffffu, c[ip][j][0], urow * 4 + quad); u[kk][j][1] = __shfl_sync(0xffffffffu, c[ip][j][1], urow * 4 + quad);
                     }
                 }
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                    for (int j = 0; j < NT; ++j)
+#pragma unroll
+                        for (int i = 0; i < MT; ++i) { c[i][j][0] = fma(-l[kk][i], u[kk][j][0], c[i][j][0]); c[i][j][1] = fma(-l[kk][i], u[kk][j][1], c[i][j][1]); }
             } else {
                 // A fragment of tile row i: A[row][k = quad] = −2⁻⁶·C[8i + row][4p + quad]  → owner quad (off+quad)/2, element (off+quad)%2
                 double a[MT], b[NT];
