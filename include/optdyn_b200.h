@@ -128,6 +128,7 @@ typedef struct od_gather_desc {
     uint32_t* block_counter;
     uint64_t* epoch_dev;
     uint64_t epoch;
+    uint64_t multicast_flags;   /* multicast alias of the flag arrays, or 0: the epoch is then published by one multimem.st */
 } od_gather_desc;
 int od_step_grad_packed_gather_ex_device(od_handle* hd, int B, const double* in, const od_gather_desc* gather, int32_t* status, int32_t* iters);
 

@@ -21,7 +21,7 @@ c_int32_p = C.POINTER(C.c_int32)
 class od_gather_desc(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("row0", C.c_int64), ("gather_buffers", C.POINTER(C.c_uint64)),
                 ("multicast_buffer", C.c_uint64), ("flag_buffers", C.POINTER(C.c_uint64)), ("block_counter", C.c_void_p),
-                ("epoch_dev", C.c_void_p), ("epoch", C.c_uint64)]
+                ("epoch_dev", C.c_void_p), ("epoch", C.c_uint64), ("multicast_flags", C.c_uint64)]
 
 
 class od_options(C.Structure):

@@ -913,9 +913,15 @@ struct StepArgs {
     // sync_epoch == 0: the epoch lives on the device — sync_epoch_dev (this rank's u64, zero before the first launch) is advanced by
     // one per launch by the last block, so a CUDA graph holding such launches can be replayed (every rank replays the same launches).
     unsigned long long* sync_epoch_dev;
+    // Persistent sweep (contact_sweep_kernel / contact_ift_kernel): work_queue = a zeroed counter in device memory from which the
+    // groups claim problem indices; z_snapshots = B × NZ doubles, the iterate of every problem at its gradient tolerance, handed from
+    // the sweep kernel to the IFT kernel.
+    unsigned int* work_queue;
+    double* z_snapshots;
     // NVLink multicast alias of the gather buffers (torch symmetric memory multicast_ptr; null = per-peer stores): ONE multimem.st
     // per 16 bytes reaches the gather buffer of every rank — this one included — and NVSwitch does the replication.
     double* mc_out;
+    unsigned long long* mc_flags;                              // multicast alias of the flag arrays (or null): one store publishes the epoch everywhere
     SolverOpts opts;
 };
 
@@ -950,6 +956,34 @@ OD_HD bool block_or(bool p) {
 #else
     return warp_any(p);
 #endif
+}
+
+// Data vector θ and the initial configuration of problem i, every lane loading every value (no collectives: callable from
+// divergent code).  Same arithmetic as the prologue of contact_step_one.
+template <class M>
+OD_HD void load_problem_plain(const StepArgs& a, const int i, double* th, double* q2v) {
+    constexpr int NQ = M::NQ, NU = M::NU;
+    const long long ig = a.eta ? a.eta_i0 + i : i;
+    const int src = a.eta ? (int)(ig / (a.n_eta + 1)) : i;
+    const int pert = a.eta ? (int)(ig % (a.n_eta + 1)) : 0;
+    const double* p1 = a.q1 + (size_t)src * a.in_stride_q;
+    const double* p2 = a.q2 + (size_t)src * a.in_stride_q;
+    const double* pu = a.u + (size_t)src * a.in_stride_u;
+    const double* pe = (pert > 0) ? a.eta + (size_t)(pert - 1) * (2 * NQ + NU) : nullptr;
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) {
+        double x1 = p1[k], x2 = p2[k];
+        if (pe) { x1 += pe[k]; x2 += pe[NQ + k]; }
+        const double v1 = a.in_vel ? x1 : (x2 - x1) / a.h;
+        th[k] = x2 - a.h * v1;
+        th[NQ + k] = x2;
+        q2v[k] = x2;
+    }
+#pragma unroll
+    for (int k = 0; k < NU; ++k) th[2 * NQ + k] = pe ? pu[k] + pe[2 * NQ + k] : pu[k];
+#pragma unroll
+    for (int k = 0; k < M::NF; ++k) th[2 * NQ + NU + k] = a.fric[k];
+    th[M::NTH - 1] = a.h;
 }
 
 template <class M, int G, int PPB, bool REG = false, bool BSYNC = false>
@@ -1265,10 +1299,17 @@ __global__ void __launch_bounds__(G * PPB, OD_MIN_BLOCKS) contact_step_kernel(co
             const unsigned prev = atomicAdd(a.sync_counter, 1u);
             if (prev == gridDim.x - 1) {                    // last block of this rank: every row of the shard is on its way / there
                 *a.sync_counter = 0u;                       // ready for the next launch (stream-ordered)
-                __threadfence_system();
                 const unsigned long long epoch = a.sync_epoch ? a.sync_epoch : *a.sync_epoch_dev + 1ull;
-                for (int p = 0; p < a.n_peers; ++p)
-                    if (p != a.self_rank) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.sync_flags[p] + a.self_rank), "l"(epoch) : "memory");
+                // ONE system-scope fence, then the flags go out as relaxed stores that travel concurrently (fence + relaxed store =
+                // release; a st.release per peer is a fence per peer: each waits for the previous flag's round trip — at 8 ranks the
+                // seven sequential releases cost more than the rest of the barrier) — or as a single multicast store.
+                __threadfence_system();
+                if (a.mc_flags) {
+                    asm volatile("multimem.st.relaxed.sys.global.u64 [%0], %1;" ::"l"(a.mc_flags + a.self_rank), "l"(epoch) : "memory");
+                } else {
+                    for (int p = 0; p < a.n_peers; ++p)
+                        if (p != a.self_rank) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(a.sync_flags[p] + a.self_rank), "l"(epoch) : "memory");
+                }
                 for (int p = 0; p < a.n_peers; ++p) {
                     if (p == a.self_rank) continue;
                     unsigned long long v;
@@ -1280,13 +1321,185 @@ __global__ void __launch_bounds__(G * PPB, OD_MIN_BLOCKS) contact_step_kernel(co
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent, block-phased sweep for the models whose loop does not fit the instruction cache (planar push: 108 KB).
+//
+// Measured on B200 (profiles/r02e_*, r02g_*): with one-warp blocks, 8 unsynchronised warps per SM each stream the loop from L2 —
+// 6 stall cycles per issued instruction waiting for instructions; phasing the warps of a 256-thread block with barriers removes
+// those stalls, but a block that ends with its slowest problem drains its SM (and 0.5 % of the planar-push batch runs 100
+// iterations).  Here both are kept: one resident block per SM, all its warps walk the state machine in phase (the two votes go
+// through __syncthreads_or), and a GROUP whose problem has finished claims the next problem index from an atomic queue at the top
+// of the next pass — a straggler then holds one group slot, not a block.  The IFT is not run inside the loop (it would serialise
+// every pass behind whichever warp happens to differentiate): the sweep kernel leaves q3, the status words and the iterate at the
+// gradient tolerance (z_snapshots), and contact_ift_kernel — naturally in phase, every problem needs exactly one pass —
+// differentiates all problems afterwards.  Per problem the arithmetic is that of contact_step_one, operation for operation: the
+// results are bit-identical (tests/test_gpu_parity.py).
+template <class M, int G, int PPB>
+__global__ void __launch_bounds__(G * PPB) contact_sweep_kernel(const StepArgs a) {
+#ifdef __CUDA_ARCH__
+    typedef ContactIP<M, G, PPB, true> IP;
+    constexpr int NQ = M::NQ;
+    static_assert((G * PPB) % 32 == 0 && !OD_INPLACE_Z, "whole warps; two-copy iterate update");
+    extern __shared__ __align__(16) double od_smem[];
+    const int slot = threadIdx.x / G, g = threadIdx.x % G, lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    double* ws = od_smem + slot * IP::WS_SLOT;
+    double th[M::NTH];
+    typename IP::Z z, D, zc;
+    typename IP::Lin L;
+    L.ws = ws; L.g = g; L.gmask = full; L.ok = true;
+    double trc[IP::NTC1], trv[IP::NTV1];
+    double r_vio = 0.0, k_vio = 0.0, alpha = 0.0;
+    bool first = true, eval_done = true, grad_done = true, active = false, have = false;
+    int it = 0, ls = 0, it_e = 0, it_g = 0, st_e = 0, st_g = 0, i = 0;
+    {
+        double q0[NQ];
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) q0[k] = 0.0;
+        IP::init_z(q0, z);
+#pragma unroll
+        for (int k = 0; k < M::NTH; ++k) th[k] = 1.0;
+        M::trig_const(th, trc);
+        D = z; zc = z;
+    }
+    // the finished problem's status words; its q3 and gradient snapshot have been written when they were taken
+    auto finish = [&]() {
+        if (g == 0) {
+            if (a.status) a.status[i] = st_e | (st_g << 4);
+            if (a.iters) a.iters[i] = it_e | (it_g << 16);
+        }
+        active = false; have = false;
+    };
+    for (;;) {
+        // ---- groups without a problem claim the next index
+        int claim = -1;
+        if (!have && g == 0) claim = (int)atomicAdd(a.work_queue, 1u);
+        claim = __shfl_sync(full, claim, lane & ~(G - 1));
+        if (!have && claim >= 0 && claim < a.B) {
+            i = claim;
+            double q2v[NQ];
+            load_problem_plain<M>(a, i, th, q2v);
+            IP::init_z(q2v, z);
+            M::trig_const(th, trc);
+            D = z; alpha = 0.0; r_vio = 0.0; k_vio = 0.0;
+            first = true; eval_done = !a.want_eval; grad_done = !a.want_grad; active = true; have = true;
+            it = 0; ls = 0; it_e = 0; it_g = 0; st_e = 0; st_g = 0;
+        }
+        // ---- candidate z − αΔ and its residual
+        typename IP::R rc; double rv2 = 0.0, kv2 = 0.0;
+        bool retry = false;
+        if (warp_any(active)) {
+            IP::candidate(z, D, alpha, zc);
+            M::trig_var(zc.q, th, trv);
+            IP::residual(zc, th, trc, trv, rc, rv2, kv2);
+            retry = active && !(first || rv2 <= r_vio || kv2 <= k_vio || ls >= a.opts.max_ls);
+            if (retry) { alpha *= a.opts.ls_scale; ++ls; }
+        }
+        if (block_or(retry)) continue;
+        // ---- accepted iterate: termination tests (a group's lanes agree on every one of these; the warp's groups may not: the
+        // snapshot's group barriers are warp barriers, so it is taken by whole warps with the other groups masked)
+        bool take_snapshot = false, done_now = false;
+        if (active) {
+            z = zc; r_vio = rv2; k_vio = kv2;
+            if (!first) ++it;
+            first = false;
+            const bool bad = !IP::finite(z, r_vio, k_vio);
+            const bool capped = it >= a.opts.max_iter;
+            const bool rok = r_vio < a.opts.r_tol;
+            const bool conv_e = rok && (k_vio < a.opts.kappa_eval_tol);
+            const bool conv_g = rok && (k_vio < a.opts.kappa_grad_tol);
+            if (!eval_done && (conv_e || capped || bad)) {
+                eval_done = true; it_e = it; st_e = bad ? ST_FAIL : (conv_e ? ST_OK : ST_MAXIT);
+                if (a.q3 && g == 0) {
+                    double* o = a.q3 + (size_t)i * a.out_stride_q3;
+#pragma unroll
+                    for (int k = 0; k < NQ; ++k) o[k] = z.q[k];
+                }
+            }
+            if (!grad_done && (conv_g || capped || bad)) {
+                grad_done = true; it_g = it; st_g = bad ? ST_FAIL : (conv_g ? ST_OK : ST_MAXIT);
+                take_snapshot = true;
+            }
+            done_now = bad || capped || (eval_done && grad_done);
+        }
+        if (warp_any(take_snapshot)) {
+            IP::store_z(L, z);                                  // (groups that are not taking one rewrite their own workspace: harmless)
+            L.sync();
+            if (take_snapshot) {
+                double* dst = a.z_snapshots + (size_t)i * IP::NZ;
+                for (int e = g; e < IP::NZ; e += G) dst[e] = ws[IP::ROFF_ZS + e];
+            }
+            L.sync();
+        }
+        if (done_now) finish();
+        // ---- anything left for this block?  (a group without a problem will claim one at the top if the queue still has any)
+        bool more = false;
+        if (!have && g == 0) more = *reinterpret_cast<volatile unsigned int*>(a.work_queue) < (unsigned)a.B;
+        if (!block_or(active || more)) break;
+        if (!warp_any(active)) continue;
+        // ---- Newton system at z, direction, step length
+        IP::linearize(z, th, trc, trv, rc, L);
+        bool failed = false;
+        if (active && !L.ok) {
+            if (!eval_done) { st_e = ST_FAIL; it_e = it; eval_done = true; }
+            if (!grad_done) { st_g = ST_FAIL; it_g = it; grad_done = true; failed = true; }
+            active = false;
+        }
+        IP::direction(L, z, rc, r_vio, k_vio, D, alpha);
+        if (!active) alpha = 0.0;
+        ls = 0;
+        if (warp_any(failed)) {                                  // singular Newton system: the IFT is still attempted at this iterate
+            IP::store_z(L, z);
+            L.sync();
+            if (failed) {
+                double* dst = a.z_snapshots + (size_t)i * IP::NZ;
+                for (int e = g; e < IP::NZ; e += G) dst[e] = ws[IP::ROFF_ZS + e];
+            }
+            L.sync();
+        }
+        if (have && !active) { L.ok = true; finish(); }
+    }
+#endif
+}
+
+// IFT at the snapshots of contact_sweep_kernel: one group per problem, ordinary grid.  Writes the Jacobian blocks and folds a failed
+// factorisation into the gradient nibble of the status word.
+template <class M, int G, int PPB>
+__global__ void __launch_bounds__(G * PPB) contact_ift_kernel(const StepArgs a) {
+#ifdef __CUDA_ARCH__
+    typedef ContactIP<M, G, PPB, true> IP;
+    constexpr int NQ = M::NQ;
+    static_assert(M::ROBUST_IFT, "the persistent sweep is instantiated for the models with the rank-revealing IFT");
+    extern __shared__ __align__(16) double od_smem[];
+    const int slot = threadIdx.x / G, g = threadIdx.x % G;
+    int i = blockIdx.x * PPB + slot;
+    if (i >= a.B) i = a.B - 1;
+    double* ws = od_smem + slot * IP::WS_SLOT;
+    typename IP::Lin L;
+    L.ws = ws; L.g = g; L.gmask = 0xffffffffu; L.ok = true;
+    double th[M::NTH], q2v[NQ], trc[IP::NTC1], trv[IP::NTV1];
+    load_problem_plain<M>(a, i, th, q2v);
+    M::trig_const(th, trc);
+    const double* src = a.z_snapshots + (size_t)i * IP::NZ;
+    for (int e = g; e < IP::NZ; e += G) ws[IP::ROFF_ZS + e] = src[e];
+    L.sync();
+    typename IP::Z z;
+    IP::load_z(L, z);
+    M::trig_var(z.q, th, trv);
+    IP::assemble(z, th, trc, trv, L);
+    const bool ok = IP::sensitivities_robust(L, z, th, trc, trv, a.dq1 + (size_t)i * a.out_stride_dq, a.dq2 + (size_t)i * a.out_stride_dq,
+                                             a.du + (size_t)i * a.out_stride_du);
+    if (!ok && g == 0 && a.status) a.status[i] = (a.status[i] & 15) | (ST_FAIL << 4);
+#endif
+}
+
 // A rank whose shard is empty still has to take part in the fused cross-GPU barrier: publish the epoch, wait for the peers.
 static __global__ void gather_sync_only_kernel(const StepArgs a) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    __threadfence_system();
     const unsigned long long epoch = a.sync_epoch ? a.sync_epoch : *a.sync_epoch_dev + 1ull;
+    __threadfence_system();
     for (int p = 0; p < a.n_peers; ++p)
-        if (p != a.self_rank) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.sync_flags[p] + a.self_rank), "l"(epoch) : "memory");
+        if (p != a.self_rank) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(a.sync_flags[p] + a.self_rank), "l"(epoch) : "memory");
     for (int p = 0; p < a.n_peers; ++p) {
         if (p == a.self_rank) continue;
         unsigned long long v;
@@ -1335,7 +1548,7 @@ OD_HD void contact_rollout_one(const RolloutArgs& ra, const int r, double* ws, c
     for (int k = 0; k < 4; ++k) a.fric[k] = ra.fric[k];
     a.want_eval = 1; a.want_grad = 0; a.eta = nullptr; a.n_eta = 0; a.eta_i0 = 0;
     a.n_peers = 0; a.self_rank = 0; a.gather_row0 = 0; a.gather_width = 0;
-    a.packed_out = 0; a.in_packed = 0; a.in_vel = 0; a.sync_counter = nullptr; a.sync_epoch = 0; a.sync_epoch_dev = nullptr; a.mc_out = nullptr;
+    a.packed_out = 0; a.in_packed = 0; a.in_vel = 0; a.sync_counter = nullptr; a.sync_epoch = 0; a.sync_epoch_dev = nullptr; a.mc_out = nullptr; a.mc_flags = nullptr; a.work_queue = nullptr; a.z_snapshots = nullptr;
     a.opts = ra.opts;
     const double alpha = ra.alpha ? ra.alpha[r] : 1.0;
     const double* ub = ra.ubar + (size_t)r * ra.ubar_stride;

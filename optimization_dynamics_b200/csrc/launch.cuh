@@ -49,13 +49,62 @@ inline bool reg_path() {
     return v != 0;
 }
 
+// Kernels launched by the last launch_contact call of this thread (the persistent sweep is two kernels): od_launch_count bookkeeping.
+inline int& last_launch_kernels() { static thread_local int n = 1; return n; }
+
+// OD_PERSIST (default 1): persistent block-phased sweep + separate IFT kernel for the models with the rank-revealing IFT, from
+// this many problems on (1 = default threshold 4096, 0 = never, n = from n problems).  Needs the scratch the C ABI layer provides
+// (work_queue, z_snapshots) and no fused gather.
+inline int persist_min_batch() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("OD_PERSIST"); v = e ? atoi(e) : 1; if (v == 1) v = 4096; }
+    return v;
+}
+template <class M, int G, int PPB>
+static inline cudaError_t launch_contact_persistent(const StepArgs& a, cudaStream_t s) {
+    typedef ContactIP<M, G, PPB, true> IP;
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    constexpr size_t smem = sizeof(double) * PPB * IP::WS;
+    cudaError_t e = cudaMemsetAsync(a.work_queue, 0, sizeof(unsigned int), s);
+    if (e != cudaSuccess) return e;
+    if (smem > 48 * 1024) {
+        if ((e = cudaFuncSetAttribute(contact_sweep_kernel<M, G, PPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    }
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, contact_sweep_kernel<M, G, PPB>, G * PPB, smem);
+    if (per_sm < 1) per_sm = 1;
+    int grid = sms * per_sm;
+    const int need = (a.B + PPB - 1) / PPB;
+    if (grid > need) grid = need;
+    contact_sweep_kernel<M, G, PPB><<<grid, G * PPB, smem, s>>>(a);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    last_launch_kernels() = 1;
+    if (a.want_grad && a.dq1) {
+        constexpr int PPB2 = 32 / G;                          // one warp per block: the IFT kernel is short and phased by construction
+        constexpr size_t smem2 = sizeof(double) * PPB2 * ContactIP<M, G, PPB2, true>::WS;
+        if (smem2 > 48 * 1024) {
+            if ((e = cudaFuncSetAttribute(contact_ift_kernel<M, G, PPB2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)) != cudaSuccess) return e;
+        }
+        contact_ift_kernel<M, G, PPB2><<<(a.B + PPB2 - 1) / PPB2, G * PPB2, smem2, s>>>(a);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        last_launch_kernels() = 2;
+    }
+    return cudaSuccess;
+}
+
 // WIDE: models large enough for 8 lanes; REGOK: models whose IFT runs on the register path (not the rank-revealing one)
 template <class M, bool WIDE, bool REGOK>
 static inline cudaError_t launch_contact(const StepArgs& a, cudaStream_t s) {
     const int lanes = lanes_for(a.B, M::ROBUST_IFT);
+    last_launch_kernels() = 1;
     if constexpr (REGOK) {
         if (reg_path()) {
             if constexpr (WIDE && M::ROBUST_IFT) {
+                if (persist_min_batch() > 0 && a.B >= persist_min_batch() && a.n_peers <= 1 && a.work_queue && (!a.want_grad || !a.dq1 || a.z_snapshots)) {
+                    if (lanes == 16) return launch_contact_persistent<M, 16, 16>(a, s);
+                    return launch_contact_persistent<M, 8, 32>(a, s);
+                }
                 // a gather with peers keeps one-warp blocks (the fused barrier counts blocks as they finish; rows should leave early)
                 if (bsync_min_batch() > 0 && a.B >= bsync_min_batch() && lanes == 8 && a.n_peers <= 1) return launch_contact_cfg<M, 8, 32, true, true>(a, s);
             }

@@ -100,7 +100,7 @@ struct od_handle {
     od_options opts;
     double params[4];
     cudaStream_t stream; bool own_stream;
-    DevBuf in, out, st, aux, aux2;
+    DevBuf in, out, st, aux, aux2, sweep;      // sweep: work queue + iterate snapshots of the persistent sweep (planar push)
     PinBuf hin, hout;
     int64_t launches;
 };
@@ -172,7 +172,7 @@ void od_destroy(od_handle* hd) {
     if (!hd) return;
     cudaSetDevice(hd->device);
     cudaStreamSynchronize(hd->stream);
-    hd->in.release(); hd->out.release(); hd->st.release(); hd->aux.release(); hd->aux2.release();
+    hd->in.release(); hd->out.release(); hd->st.release(); hd->aux.release(); hd->aux2.release(); hd->sweep.release();
     hd->hin.release(); hd->hout.release();
     if (hd->own_stream) cudaStreamDestroy(hd->stream);
     delete hd;
@@ -213,6 +213,13 @@ static int launch_step(od_handle* hd, StepArgs& a, bool grad_sim_q3 = false) {
     a.opts.r_tol = hd->opts.r_tol; a.opts.kappa_eval_tol = hd->opts.kappa_eval_tol; a.opts.kappa_grad_tol = hd->opts.kappa_grad_tol;
     a.opts.ls_scale = hd->opts.ls_scale; a.opts.max_iter = hd->opts.max_iter; a.opts.max_ls = hd->opts.max_ls;
     if (grad_sim_q3) a.opts.kappa_eval_tol = hd->opts.kappa_grad_tol;
+    if (hd->model == OD_PLANAR_PUSH && a.n_peers <= 1) {         // scratch of the persistent sweep (launch.cuh decides whether it is used)
+        Dims d; dims_of(hd->model, &d);
+        if (hd->sweep.reserve(256 + sizeof(double) * (size_t)d.nz * a.B) == cudaSuccess) {
+            a.work_queue = (unsigned int*)hd->sweep.p;
+            a.z_snapshots = (double*)((char*)hd->sweep.p + 256);
+        }
+    }
     cudaError_t e;
     switch (hd->model) {
         case OD_ACROBOT_IMPACT: e = od_launch_step_acrobot_impact(a, hd->stream); break;
@@ -224,7 +231,7 @@ static int launch_step(od_handle* hd, StepArgs& a, bool grad_sim_q3 = false) {
         default: return fail("this entry point needs a contact model handle (not OD_ROCKET)");
     }
     if (e != cudaSuccess) return fail("contact_step_kernel launch", e);
-    hd->launches++;
+    hd->launches += last_launch_kernels();
     return 0;
 }
 
@@ -287,7 +294,10 @@ int od_step_grad_packed_gather_ex_device(od_handle* hd, int B, const double* in,
     }
     a.packed_out = aligned ? 1 : 0;
     a.mc_out = (aligned && outw % 2 == 0) ? (double*)g->multicast_buffer : nullptr;
-    if (sync) { a.sync_counter = g->block_counter; a.sync_epoch = g->epoch; a.sync_epoch_dev = (unsigned long long*)g->epoch_dev; }
+    if (sync) {
+        a.sync_counter = g->block_counter; a.sync_epoch = g->epoch; a.sync_epoch_dev = (unsigned long long*)g->epoch_dev;
+        a.mc_flags = (unsigned long long*)g->multicast_flags;
+    }
     if (B <= 0) {
         if (!sync) return 0;
         // empty shard (ragged split, B_total < world): the peers still wait for this rank's flag

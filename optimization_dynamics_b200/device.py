@@ -180,6 +180,12 @@ class FusedGather:
             self.flags.zero_()
             self.flag_handle = symm_mem.rendezvous(self.flags, grp)
             self.flag_ptrs = (C.c_uint64 * self.world)(*[int(p) for p in self.flag_handle.buffer_ptrs])
+            self.mc_flags = 0
+            if self.multicast:
+                try:
+                    self.mc_flags = int(self.flag_handle.multicast_ptr or 0)
+                except Exception:
+                    self.mc_flags = 0
             self.counter = torch.zeros(4, dtype=torch.int64, device=dev)       # [0]: block counter (u32), [1]: epoch (u64), device side
             torch.cuda.synchronize()
             self.flag_handle.barrier(channel=0)          # every rank's flags are zero before anyone publishes epoch 1
@@ -212,6 +218,7 @@ class FusedGather:
             g.block_counter = self.counter.data_ptr()
             g.epoch_dev = self.counter.data_ptr() + 8
             g.epoch = 0
+            g.multicast_flags = self.mc_flags
         self.buf = self.bufs[which]
         g.gather_buffers = self.ptrs[which]
         g.multicast_buffer = self.mc[which] if self.multicast else 0

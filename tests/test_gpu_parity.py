@@ -447,3 +447,28 @@ def test_user_model_on_the_gpu(od, tmp_path):
     eg = max(np.abs(d1 - h1.transpose(0, 2, 1))[ok].max(), np.abs(d2 - h2.transpose(0, 2, 1))[ok].max(), np.abs(du - hu.transpose(0, 2, 1))[ok].max())
     print("user model on the GPU vs host tier: max|q3| %.2e  max|grad| %.2e  converged %.4f" % (np.abs(q3 - hq3)[ok].max(), eg, ok.mean()))
     assert eg <= GRAD_TOL
+
+
+def test_persistent_sweep_is_bitwise_the_per_warp_kernel(od):
+    """Planar push batches of 4096 problems and more run as a persistent, block-phased sweep (groups refill from an atomic queue)
+    plus a separate IFT kernel (csrc/contact_ip.cuh: contact_sweep_kernel / contact_ift_kernel); smaller batches run the per-warp
+    kernel.  Per problem the arithmetic is the same, operation for operation: the same problems solved in one large batch and in
+    small pieces must agree bit for bit — q3, all three Jacobian blocks, status words — including the problems that run into the
+    iteration cap, and with f-only / gradient-only requests."""
+    gen, h, ke, kg, fric, _ = CONFIGS["planar_push"]
+    B = 4700
+    q1, q2, u = gen(B, h=h, seed=17)
+    dyn = make_dyn(od, "planar_push")
+    n0 = dyn.launch_count()
+    big = dyn.step_grad_batch(q1, q2, u)
+    assert dyn.launch_count() - n0 == 2                    # sweep kernel + IFT kernel
+    parts = [dyn.step_grad_batch(q1[lo:lo + 1175], q2[lo:lo + 1175], u[lo:lo + 1175]) for lo in range(0, B, 1175)]
+    for k in range(5):
+        small = np.concatenate([p[k] for p in parts])
+        assert np.array_equal(big[k], small, equal_nan=True), k
+    assert ((big[4] & 15) == 1).sum() >= 1                 # the batch does contain problems that hit max_iter
+    q3only, st3 = dyn.step_batch(q1, q2, u)
+    assert np.array_equal(q3only, big[0], equal_nan=True) and np.array_equal(st3, big[4] & 15)
+    again = dyn.step_grad_batch(q1, q2, u)                 # the queue counter is reset by every launch
+    for k in range(5):
+        assert np.array_equal(big[k], again[k], equal_nan=True)
