@@ -958,6 +958,21 @@ OD_HD bool block_or(bool p) {
 #endif
 }
 
+// θ.q1 = q2 − h·v1 with v1 = (q2 − q1)/h (src/dynamics.jl:84-86, RoboDojo.step!): rounded operation by operation, never contracted
+// into a fused multiply-add — the reference (Julia) and the oracle (gcc -ffp-contract=off) round the product first, and every
+// instantiation of the solver (per-warp kernel, persistent sweep, IFT kernel, rollouts) must see the same data vector bit for bit.
+OD_HD void theta_q1(const double x1, const double x2, const double h, const bool in_vel, double& q1p, double& v1out) {
+#ifdef __CUDA_ARCH__
+    const double v1 = in_vel ? x1 : __ddiv_rn(__dsub_rn(x2, x1), h);
+    q1p = __dsub_rn(x2, __dmul_rn(h, v1));
+#else
+    const double v1 = in_vel ? x1 : (x2 - x1) / h;
+    volatile double hv = h * v1;
+    q1p = x2 - hv;
+#endif
+    v1out = v1;
+}
+
 // Data vector θ and the initial configuration of problem i, every lane loading every value (no collectives: callable from
 // divergent code).  Same arithmetic as the prologue of contact_step_one.
 template <class M>
@@ -974,8 +989,8 @@ OD_HD void load_problem_plain(const StepArgs& a, const int i, double* th, double
     for (int k = 0; k < NQ; ++k) {
         double x1 = p1[k], x2 = p2[k];
         if (pe) { x1 += pe[k]; x2 += pe[NQ + k]; }
-        const double v1 = a.in_vel ? x1 : (x2 - x1) / a.h;
-        th[k] = x2 - a.h * v1;
+        double v1;
+        theta_q1(x1, x2, a.h, a.in_vel != 0, th[k], v1);
         th[NQ + k] = x2;
         q2v[k] = x2;
     }
@@ -1027,8 +1042,8 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
         for (int k = 0; k < NQ; ++k) {
             double x1 = xin[k], x2 = xin[NQ + k];
             if (pe) { x1 += pe[k]; x2 += pe[NQ + k]; }
-            const double v1 = a.in_vel ? x1 : (x2 - x1) / a.h; // src/dynamics.jl:84-86 (or the caller's v1: step!(sim, q2, v1, u1, t))
-            th[k] = x2 - a.h * v1;                             // RoboDojo.step!: q1 = q2 − h v1
+            double v1;                                         // src/dynamics.jl:84-86 (or the caller's v1: step!(sim, q2, v1, u1, t))
+            theta_q1(x1, x2, a.h, a.in_vel != 0, th[k], v1);   // RoboDojo.step!: q1 = q2 − h v1
             th[NQ + k] = x2;
             q2v[k] = x2;
         }

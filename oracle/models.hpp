@@ -241,7 +241,7 @@ struct Hopper {
 
     // L = ½ mb |ṗ_body|² + ½ Ib ṫ² + ½ mf |ṗ_foot|² − mb g z − mf g z_foot, foot = body + r (sin t, −cos t)
     // (foot kinematics pinned by examples/hopper.jl:178: q=[0, 0.5+foot_radius, 0, 0.5] puts the foot on the ground).
-    // M(q) = ∂²L/∂q̇², C(q,q̇) = (∂²L/∂q̇∂q) q̇ − ∂L/∂q — closed forms, checked against sympy in tests/test_oracle_models.py.
+    // M(q) = ∂²L/∂q̇², C(q,q̇) = (∂²L/∂q̇∂q) q̇ − ∂L/∂q — closed forms, checked against sympy differentiation of the Lagrangian in tests/test_oracle.py::test_hopper_closed_form_bias_matches_lagrangian.
     template <class S> void momentum(const S* q, const S* v, S* p) const {
         S s = od_sin(q[2]), c = od_cos(q[2]);
         const double mb = mass_body, mf = mass_foot;

@@ -26,6 +26,12 @@ CONFIGS = {
 }
 
 
+# floor on the fraction of a benchmark batch that takes part in the 1e-8 / 1e-6 comparison, per model (measured: hopper 1.000 / 0.9998,
+# cartpole 1.000, acrobot 1.000, planar push 0.995 — its 0.4–0.5 % stragglers run into max_iter in the oracle as well)
+MIN_COMPARABLE = {"hopper": 0.999, "cartpole_friction": 0.995, "cartpole_frictionless": 0.995, "acrobot_impact": 0.995, "acrobot_nominal": 0.995,
+                  "planar_push": 0.985}
+
+
 def oracle_pair(O, name, q1, q2, u):
     gen, h, ke, kg, fric, _ = CONFIGS[name]
     e = O.step_batch(name, q1, q2, u, h, ke, False, fric=fric)
@@ -40,8 +46,14 @@ def compare(name, e, g, q3, d1, d2, du, st_eval, st_grad, min_fraction=0.97, gra
     # final iterate is not reproducible across implementations of the same algorithm
     ok_e = (e["status"] == 0) & (st_eval == 0) & (e["margin"] > MARGIN_MIN) & (e["iters"] <= 30)
     ok_g = (g["status"] == 0) & (st_grad == 0) & (g["margin"] > MARGIN_MIN) & (g["ift_spread"] < 1e-8) & (g["iters"] <= 30)
-    assert ok_e.mean() >= min_fraction, "%s: only %.3f of eval solves comparable" % (name, ok_e.mean())
-    assert ok_g.mean() >= min_fraction, "%s: only %.3f of grad solves comparable" % (name, ok_g.mean())
+    # what the rule leaves out, per cause (printed with -s; asserted against the per-model floor below)
+    print("%s: comparable eval %.4f / grad %.4f of %d  [not converged (oracle) %.4f, fragile decision %.4f, > 30 iterations %.4f, IFT not determined %.4f; "
+          "oracle iterations mean %.2f max %d]" % (name, ok_e.mean(), ok_g.mean(), B, ((e["status"] != 0) | (g["status"] != 0)).mean(),
+                                                   ((e["margin"] <= MARGIN_MIN) | (g["margin"] <= MARGIN_MIN)).mean(), (e["iters"] > 30).mean(),
+                                                   (g["ift_spread"] >= 1e-8).mean(), e["iters"].mean(), e["iters"].max()))
+    min_fraction = max(min_fraction, MIN_COMPARABLE.get(name, min_fraction))
+    assert ok_e.mean() >= min_fraction, "%s: only %.4f of eval solves comparable" % (name, ok_e.mean())
+    assert ok_g.mean() >= min_fraction, "%s: only %.4f of grad solves comparable" % (name, ok_g.mean())
     # status must agree except on rounding-fragile samples
     assert ((e["status"] != st_eval) & (e["margin"] > MARGIN_MIN)).mean() <= 0.005
     errq = np.abs(q3 - e["q3"]).max(1)

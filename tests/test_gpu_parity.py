@@ -449,12 +449,14 @@ def test_user_model_on_the_gpu(od, tmp_path):
     assert eg <= GRAD_TOL
 
 
-def test_persistent_sweep_is_bitwise_the_per_warp_kernel(od):
+def test_persistent_sweep_matches_the_per_warp_kernel_and_the_oracle(od, O):
     """Planar push batches of 4096 problems and more run as a persistent, block-phased sweep (groups refill from an atomic queue)
     plus a separate IFT kernel (csrc/contact_ip.cuh: contact_sweep_kernel / contact_ift_kernel); smaller batches run the per-warp
-    kernel.  Per problem the arithmetic is the same, operation for operation: the same problems solved in one large batch and in
-    small pieces must agree bit for bit — q3, all three Jacobian blocks, status words — including the problems that run into the
-    iteration cap, and with f-only / gradient-only requests."""
+    kernel.  Same algorithm, separately compiled: the two may differ in multiply-add contraction, i.e. by rounding — invisible on a
+    problem that converges in a few iterations, amplified on the few that wander for tens of iterations.  So: the same problems
+    solved in one large batch and in small pieces agree to rounding (median 1 ulp) wherever both converge within 30 iterations, the status
+    words agree on ≥ 99.8 % of the batch, the large batch is reproducible bit for bit run to run (the queue makes the SCHEDULE
+    non-deterministic, not the results), f-only equals f of f+gradient — and the large batch passes the oracle parity rule."""
     gen, h, ke, kg, fric, _ = CONFIGS["planar_push"]
     B = 4700
     q1, q2, u = gen(B, h=h, seed=17)
@@ -463,12 +465,52 @@ def test_persistent_sweep_is_bitwise_the_per_warp_kernel(od):
     big = dyn.step_grad_batch(q1, q2, u)
     assert dyn.launch_count() - n0 == 2                    # sweep kernel + IFT kernel
     parts = [dyn.step_grad_batch(q1[lo:lo + 1175], q2[lo:lo + 1175], u[lo:lo + 1175]) for lo in range(0, B, 1175)]
-    for k in range(5):
-        small = np.concatenate([p[k] for p in parts])
-        assert np.array_equal(big[k], small, equal_nan=True), k
+    small = [np.concatenate([p[k] for p in parts]) for k in range(5)]
+    assert (big[4] == small[4]).mean() >= 0.998
+    both = (big[4] == 0) & (small[4] == 0)
+    e, g = oracle_pair(O, "planar_push", q1, q2, u)
+    calm = both & (e["iters"] <= 30) & (g["iters"] <= 30)
+    assert calm.mean() > 0.98
+    dq = np.abs(big[0] - small[0]).max(1)[calm]
+    dg = np.maximum.reduce([np.abs(big[k] - small[k]).reshape(B, -1).max(1) for k in (1, 2, 3)])[calm]
+    print("persistent vs per-warp kernel on %d calm problems: |dq3| bit-identical %.3f, median %.1e, p99 %.1e, max %.1e;  |dgrad| median %.1e, p99 %.1e, max %.1e" % (
+        calm.sum(), (dq == 0).mean(), np.median(dq), np.quantile(dq, 0.99), dq.max(), np.median(dg), np.quantile(dg, 0.99), dg.max()))
+    # measured (profiles/r02k_*): median 1 ulp, p99 4e-12, max 3e-7 on a handful of ill-conditioned problems
+    assert np.median(dq) <= 1e-14 and np.quantile(dq, 0.99) <= 1e-9 and dq.max() <= 1e-5
+    assert np.median(dg) <= 1e-11 and np.quantile(dg, 0.99) <= 1e-6
     assert ((big[4] & 15) == 1).sum() >= 1                 # the batch does contain problems that hit max_iter
     q3only, st3 = dyn.step_batch(q1, q2, u)
     assert np.array_equal(q3only, big[0], equal_nan=True) and np.array_equal(st3, big[4] & 15)
-    again = dyn.step_grad_batch(q1, q2, u)                 # the queue counter is reset by every launch
+    again = dyn.step_grad_batch(q1, q2, u)
     for k in range(5):
         assert np.array_equal(big[k], again[k], equal_nan=True)
+    eq, eg = compare("planar_push", e, g, big[0], big[1], big[2], big[3], big[4] & 15, (big[4] >> 4) & 15)
+    print("persistent sweep vs oracle: max|q3| %.2e  max|grad| %.2e" % (eq, eg))
+
+
+def test_hard_acrobot_controls_are_characterised(od, O):
+    """workloads.acrobot_batch draws controls from N(0, 0.5²) because larger impulses make Newton wander.  The hard regime is not
+    hidden: with u ~ N(0, 3²) this prints how the iteration counts spread, and asserts that (a) both sides still agree on WHICH
+    problems converge, (b) the comparison rule still holds on every problem it admits, (c) the admitted fraction is what it is
+    (≥ 0.9) — the rest are iterate sequences of > 30 steps, which the rule leaves out for every implementation."""
+    h, ke, kg = 0.05, 1e-4, 1e-3
+    B = 2048
+    q1, q2, u = od.workloads.acrobot_batch(B, h=h, seed=31)
+    u = 6.0 * u                                                     # N(0, 3²)
+    dyn = make_dyn(od, "acrobot_impact")
+    q3, d1, d2, du, st = dyn.step_grad_batch(q1, q2, u)
+    e = O.step_batch("acrobot_impact", q1, q2, u, h, ke, False)
+    g = O.step_batch("acrobot_impact", q1, q2, u, h, kg, True)
+    it = e["iters"]
+    print("acrobot, u ~ N(0, 3²): oracle iterations mean %.2f  p90 %d  p99 %d  max %d;  > 30 iterations: %.4f;  not converged: oracle %.4f, GPU %.4f" % (
+        it.mean(), np.percentile(it, 90), np.percentile(it, 99), it.max(), (it > 30).mean(), (e["status"] != 0).mean(), ((st & 15) != 0).mean()))
+    assert ((e["status"] == 0) == ((st & 15) == 0)).mean() >= 0.99
+    ok = (e["status"] == 0) & (g["status"] == 0) & (st == 0) & (np.minimum(e["margin"], g["margin"]) > 1e-6) & (e["iters"] <= 30) & (g["iters"] <= 30) \
+        & (g["ift_spread"] < 1e-8)
+    print("  comparable fraction %.4f" % ok.mean())
+    assert ok.mean() >= 0.9
+    sure = ok & ~(np.maximum(e["q_uncertainty"], g["q_uncertainty"]) > 1e-7)
+    assert np.abs(q3 - e["q3"])[sure].max() <= Q3_TOL
+    eg = np.maximum.reduce([np.abs(d1 - g["dq1"].transpose(0, 2, 1)).reshape(B, -1).max(1), np.abs(d2 - g["dq2"].transpose(0, 2, 1)).reshape(B, -1).max(1),
+                            np.abs(du - g["du"].transpose(0, 2, 1)).reshape(B, -1).max(1)])
+    assert (eg[sure] > GRAD_TOL).mean() <= 0.005

@@ -271,11 +271,12 @@ def test_cooperative_lanes_on_the_host_match_one_lane(name, lanes, B):
 
 @pytest.mark.parametrize("name,lanes,B", [("hopper", 8, 22), ("hopper", 4, 13), ("hopper", 16, 5), ("cartpole_friction", 4, 19),
                                           ("acrobot_impact", 4, 11), ("planar_push", 16, 4), ("planar_push", 8, 6)])
-@pytest.mark.parametrize("flags,tag", [(["-DOD_EXTRACT_SMEM=1"], "_extract"), (["-DOD_EXTRACT_SMEM=1", "-DOD_INPLACE_Z=1"], "_v2z")])
+@pytest.mark.parametrize("flags,tag", [(["-DOD_EXTRACT_SMEM=0"], "_shuffle_gather")] + (
+    [(["-DOD_EXTRACT_SMEM=1", "-DOD_INPLACE_Z=1"], "_v2z")] if os.environ.get("OD_TEST_ALL_VARIANTS") else []))
 def test_prepared_mirror_variant_matches_shipped_path(name, lanes, B, flags, tag):
-    """The prepared, not shipped, variants of DESIGN.md §9 — -DOD_EXTRACT_SMEM=1 (inverse pivots and solutions through the
-    shared-memory mirror, zero multiplier in pivot rows) and on top of it -DOD_INPLACE_Z=1 (iterate advanced in place) — must
-    reproduce the shipped path bit for bit, with one lane and with cooperative lanes.  (The in-place variant differs by rounding
+    """The shipped build (-DOD_EXTRACT_SMEM=1: inverse pivots and solutions through the shared-memory mirror, zero multiplier in pivot
+    rows) against the round-1 path it replaced (-DOD_EXTRACT_SMEM=0: solution gathered by shuffles) and against the in-place iterate
+    update on top of it (-DOD_INPLACE_Z=1, measured, not shipped): bit for bit, with one lane and with cooperative lanes.  (The in-place variant differs by rounding
     only on a retried line-search step, which these batches do not contain except, rarely, on the planar push.)"""
     gen, h, ke, kg, fric, _ = CONFIGS[name]
     q1, q2, u = gen(B, h=h, seed=12)
@@ -293,16 +294,15 @@ def test_prepared_mirror_variant_matches_shipped_path(name, lanes, B, flags, tag
                 assert np.allclose(base[k], other[k], rtol=0, atol=1e-9, equal_nan=True), k
 
 
-@pytest.mark.parametrize("name,lanes,B", [("hopper", 8, 22), ("hopper", 4, 13), ("hopper", 16, 5), ("cartpole_friction", 4, 19),
-                                          ("acrobot_impact", 4, 11), ("planar_push", 16, 4), ("planar_push", 8, 6), ("planar_push", 4, 5)])
+@pytest.mark.parametrize("name,lanes,B", [("hopper", 8, 22), ("hopper", 4, 13), ("cartpole_friction", 4, 19), ("acrobot_impact", 4, 11), ("planar_push", 8, 6)])
+@pytest.mark.skipif(not os.environ.get("OD_TEST_ALL_VARIANTS"), reason="measured-and-rejected A/B variant: set OD_TEST_ALL_VARIANTS=1 to build and check it (≈ 80 s of nvcc)")
 def test_shared_memory_resident_elimination_matches_register_path(name, lanes, B):
     """GroupGJS (matrix resident in shared memory, rolled step loop — an A/B option, ContactIP::LASM; measured slower, off) against the
     register-resident GroupGJ: same arithmetic in the same order, so bit-identical, with one lane and with cooperative lanes.
-    -DOD_LA_SMEM_MIN_NR=1 builds every model on GroupGJS, -DOD_LA_SMEM_MIN_NR=99 none."""
+    -DOD_LA_SMEM_MIN_NR=1 builds every model on GroupGJS; the shipped build (99) none."""
     gen, h, ke, kg, fric, _ = CONFIGS[name]
     q1, q2, u = gen(B, h=h, seed=13)
-    with H.use_variant(["-DOD_EXTRACT_SMEM=1", "-DOD_LA_SMEM_MIN_NR=99"], "_lareg"):
-        base = H.step(name, q1, q2, u, h, ke, kg, fric=fric, reg=lanes)
+    base = H.step(name, q1, q2, u, h, ke, kg, fric=fric, reg=lanes)          # the shipped build: register-resident elimination
     with H.use_variant(["-DOD_EXTRACT_SMEM=1", "-DOD_LA_SMEM_MIN_NR=1"], "_lasm"):
         var1 = H.step(name, q1, q2, u, h, ke, kg, fric=fric, reg=1)
         var = H.step(name, q1, q2, u, h, ke, kg, fric=fric, reg=lanes)
@@ -313,12 +313,12 @@ def test_shared_memory_resident_elimination_matches_register_path(name, lanes, B
             assert np.array_equal(base[k], other[k], equal_nan=True), k
 
 
-@pytest.mark.parametrize("variant", [None, "-DOD_EXTRACT_SMEM=1"])       # (OD_INPLACE_Z only touches the contact state machine)
+@pytest.mark.parametrize("variant", [None, "-DOD_EXTRACT_SMEM=0"])       # (OD_INPLACE_Z only touches the contact state machine)
 def test_cooperative_lanes_rocket_and_rollouts_on_the_host(variant):
     """rocket_kernel_g (dense 12×12 dynamics + 10×10 cone projection + chain rule) and the closed-loop rollout template with
     cooperating lanes on emulated warps: identical to their one-lane runs, for the shipped path and the prepared variant."""
     import contextlib
-    ctx = H.use_variant([variant], "_extract") if variant else contextlib.nullcontext()
+    ctx = H.use_variant([variant], "_shuffle_gather") if variant else contextlib.nullcontext()
     x, u = W.rocket_batch(9, seed=4)
     q1, q2, _ = W.hopper_batch(6, h=0.05, seed=5)
     x1 = np.concatenate([q1, q2], axis=1)
@@ -342,10 +342,11 @@ def test_pathological_inputs_agree_across_lanes_and_variants():
     q1, q2, u = W.hopper_batch(8, h=0.05, seed=2)
     q1[1, 0] = np.nan; u[2, :] = 1e12; q2[3, 1] = -50.0; q1[4, :] = q2[4, :]; u[5, :] = np.inf; q2[6, 3] = 1e-30
     runs = [H.step("hopper", q1, q2, u, 0.05, reg=1), H.step("hopper", q1, q2, u, 0.05, reg=8)]
-    with H.use_variant(["-DOD_EXTRACT_SMEM=1"], "_extract"):
+    with H.use_variant(["-DOD_EXTRACT_SMEM=0"], "_shuffle_gather"):
         runs += [H.step("hopper", q1, q2, u, 0.05, reg=1), H.step("hopper", q1, q2, u, 0.05, reg=8)]
-    with H.use_variant(["-DOD_EXTRACT_SMEM=1", "-DOD_INPLACE_Z=1"], "_v2z"):
-        runs += [H.step("hopper", q1, q2, u, 0.05, reg=1), H.step("hopper", q1, q2, u, 0.05, reg=8)]
+    if os.environ.get("OD_TEST_ALL_VARIANTS"):
+        with H.use_variant(["-DOD_EXTRACT_SMEM=1", "-DOD_INPLACE_Z=1"], "_v2z"):
+            runs += [H.step("hopper", q1, q2, u, 0.05, reg=1), H.step("hopper", q1, q2, u, 0.05, reg=8)]
     base = runs[0]
     assert base["st_eval"][1] == 2 and base["st_eval"][5] == 2            # non-finite inputs: ST_FAIL
     assert set(base["st_eval"][[2, 3]]) <= {1, 2}                          # absurd inputs: iteration cap or failure, reported
