@@ -484,8 +484,22 @@ def test_persistent_sweep_matches_the_per_warp_kernel_and_the_oracle(od, O):
     again = dyn.step_grad_batch(q1, q2, u)
     for k in range(5):
         assert np.array_equal(big[k], again[k], equal_nan=True)
-    eq, eg = compare("planar_push", e, g, big[0], big[1], big[2], big[3], big[4] & 15, (big[4] >> 4) & 15)
-    print("persistent sweep vs oracle: max|q3| %.2e  max|grad| %.2e" % (eq, eg))
+    # against the oracle, by the comparison rule of tests/common.py — counted for BOTH kernels on this (harder, seed 17) batch: the
+    # persistent sweep may not be further from the oracle than the per-warp kernel is
+    def violations(res):
+        ok_e = (e["status"] == 0) & ((res[4] & 15) == 0) & (e["margin"] > 1e-6) & (e["iters"] <= 30)
+        ok_g = (g["status"] == 0) & (((res[4] >> 4) & 15) == 0) & (g["margin"] > 1e-6) & (g["ift_spread"] < 1e-8) & (g["iters"] <= 30)
+        errq = np.abs(res[0] - e["q3"]).max(1)
+        errg = np.maximum.reduce([np.abs(res[1] - g["dq1"].transpose(0, 2, 1)).reshape(B, -1).max(1), np.abs(res[2] - g["dq2"].transpose(0, 2, 1)).reshape(B, -1).max(1),
+                                  np.abs(res[3] - g["du"].transpose(0, 2, 1)).reshape(B, -1).max(1)])
+        vq = ok_e & (errq > Q3_TOL) & ~(e["q_uncertainty"] > 1e-7)
+        vg = ok_g & (errg > GRAD_TOL) & ~(g["q_uncertainty"] > 1e-7)
+        return int(vq.sum()), int(vg.sum()), float(ok_e.mean()), float(np.median(errq[ok_e])), float(np.median(errg[ok_g]))
+    vb, vs = violations(big), violations(small)
+    print("vs oracle (seed-17 batch of %d): persistent sweep: %d q3 / %d gradient samples outside 1e-8 / 1e-6 with a well-determined iterate (comparable %.4f, "
+          "median errors %.1e / %.1e);  per-warp kernel: %d / %d (median %.1e / %.1e)" % (B, vb[0], vb[1], vb[2], vb[3], vb[4], vs[0], vs[1], vs[3], vs[4]))
+    assert vb[0] <= vs[0] + 3 and vb[1] <= vs[1] + 3 and vb[0] <= 0.002 * B and vb[1] <= 0.005 * B
+    assert vb[3] <= 1e-10 and vb[4] <= 1e-8
 
 
 def test_hard_acrobot_controls_are_characterised(od, O):
