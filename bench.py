@@ -618,6 +618,10 @@ def main():
                                      "unit": UNIT, "timed": r["mode"], "steps": sub2.steps}
         del r
 
+    # every collective is behind us: the other ranks leave now, so that no GPU spins in an NCCL barrier while rank 0 times the CPU baseline
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank == 0:
         peak, peak_src = measured_peak()
         ms_per_step = main_res["ms"] / args.steps
@@ -655,9 +659,6 @@ def main():
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(cfg, min(B_total, 4096), seconds=args.cpu_seconds, pattern="D")
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -413,3 +413,20 @@ def test_user_model_front_end(tmp_path):
                 args_p = [ap if a is arr else a for a in (q1, q2, u)]; args_m = [am if a is arr else a for a in (q1, q2, u)]
                 fd = (step(*args_p, reg=reg, ke=1e-9, kg=1e-9)[0][0] - step(*args_m, reg=reg, ke=1e-9, kg=1e-9)[0][0]) / (2 * eps)
                 assert np.allclose(blk[0][:, j], fd, atol=2e-4), (reg, j, blk[0][:, j], fd)
+
+
+def test_bundle_prepare_inverts_the_normal_matrix_and_reports_singularity(built):
+    """od_bundle_prepare (host side of the gradient bundle, no GPU needed): (Σ η ηᵀ)⁻¹ for the shared perturbations; a coordinate that
+    no perturbation touches — where the reference's LU would silently divide by zero (src/ls.jl:52) — is reported as an error."""
+    from optimization_dynamics_b200 import _lib, workloads as W
+    L = _lib.lib()
+    ncol, N = 10, 64
+    eta = W.bundle_perturbations(ncol, N=N, eps=1e-4, seed=3)
+    hinv = np.zeros((ncol, ncol))
+    assert L.od_bundle_prepare(ncol, N, eta.ctypes.data_as(_lib.c_double_p), hinv.ctypes.data_as(_lib.c_double_p)) == 0
+    H = eta.T @ eta
+    assert np.allclose(hinv @ H, np.eye(ncol), atol=1e-9)
+    eta[:, 4] = 0.0                                                     # coordinate 4 never perturbed
+    assert L.od_bundle_prepare(ncol, N, eta.ctypes.data_as(_lib.c_double_p), hinv.ctypes.data_as(_lib.c_double_p)) != 0
+    assert b"singular" in L.od_last_error()
+    assert L.od_bundle_prepare(17, N, eta.ctypes.data_as(_lib.c_double_p), hinv.ctypes.data_as(_lib.c_double_p)) != 0     # 2nq+nu > 16 unsupported
