@@ -656,7 +656,7 @@ def main():
             extra["single_call_latency"] = single_call_latency(sw)
         if extra:
             line["extra"] = extra
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:          # (the CPU baseline is reported on rank 0 at N = 1 only)
             line["cpu_baseline"] = cpu_baseline(cfg, min(B_total, 4096), seconds=args.cpu_seconds, pattern="D")
         print(json.dumps(line), flush=True)
 
