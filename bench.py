@@ -572,7 +572,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's banner / warnings go to stderr: rank 0 prints exactly one JSON line on stdout
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # the GPU boxes export NCCL_DEBUG=VERSION, whose banner goes to stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
