@@ -559,6 +559,11 @@ def main():
             args.steps, args.warmup = 20, 3
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    # Exactly ONE line on stdout: everything any library writes to file descriptor 1 during the run (NCCL's version banner at
+    # NCCL_DEBUG=VERSION / WARN, torch warnings) is sent to stderr; the JSON line goes to the saved descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -659,7 +664,8 @@ def main():
             line["extra"] = extra
         if not args.no_cpu_baseline and world == 1:          # (the CPU baseline is reported on rank 0 at N = 1 only)
             line["cpu_baseline"] = cpu_baseline(cfg, min(B_total, 4096), seconds=args.cpu_seconds, pattern="D")
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 
 if __name__ == "__main__":
