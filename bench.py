@@ -393,8 +393,11 @@ class Sweep:
             return ("gradient_batch -> od_bundle_batch (host arrays in, dz out)" + (" — every rank runs the whole sweep (replicas)" if self.world > 1 else ""),
                     self.in_width * 8 * len(x), (self.out_width * 8 + 4) * len(x))
         x = self.x_host.numpy()
-        self.e_np = (np.ascontiguousarray(x[:, :12]), np.ascontiguousarray(x[:, 12:]))
-        return ("RocketInfo.step_batch -> od_rocket_batch (host arrays in; y, dx, du out)", 15 * 8 * self.B, (192 * 8 + 4) * self.B)
+        pin = lambda shape, dt: t.empty(shape, dtype=dt).pin_memory()        # noqa: E731
+        self.e_pin = (t.from_numpy(np.ascontiguousarray(x[:, :12])).pin_memory(), t.from_numpy(np.ascontiguousarray(x[:, 12:])).pin_memory(),
+                      pin((self.B, 12), t.float64), pin((self.B, 12, 12), t.float64), pin((self.B, 3, 12), t.float64), pin((self.B,), t.int32))
+        self.e_np = tuple(a.numpy() for a in self.e_pin)
+        return ("RocketInfo.step_batch -> od_rocket_batch (pinned host arrays in; y, dx, du, status out into pinned host arrays)", 15 * 8 * self.B, (192 * 8 + 4) * self.B)
 
     def e2e_step(self):
         kind = self.cfg["kind"]
@@ -406,7 +409,7 @@ class Sweep:
         elif kind == "bundle":
             self.od.gradient_batch(self.dyn, self.gb, *self.e_np)
         else:
-            self.info.step_batch(self.e_np[0], self.e_np[1], proj=True)
+            self.info.step_batch(self.e_np[0], self.e_np[1], proj=True, out=self.e_np[2:])
 
 
 def single_call_latency(sw, reps=200):

@@ -33,12 +33,19 @@ class RocketInfo:
         except Exception:
             pass
 
-    def step_batch(self, x, u, proj, grad=True):
-        """y[B,12], dx[B,12,12], du[B,12,3], status[B] for B problems."""
+    def step_batch(self, x, u, proj, grad=True, out=None):
+        """y[B,12], dx[B,12,12], du[B,12,3], status[B] for B problems.  `out` = (y, dx_cm, du_cm, status): caller-owned C-contiguous
+        buffers of shapes (B,12), (B,12,12), (B,3,12), (B,) — e.g. views of pinned host memory, which the copies then run from at
+        full PCIe rate; the Jacobian buffers hold the ABI's column-major blocks (the returned views are their transposes)."""
         x = _f64(x, (-1, 12)); B = x.shape[0]; u = _f64(u, (B, 3))
-        y = np.empty((B, 12)); st = np.empty(B, dtype=np.int32)
-        dx = np.empty((B, 12, 12)) if grad else None
-        du = np.empty((B, 3, 12)) if grad else None
+        if out is not None:
+            y, dx, du, st = out
+            if not grad:
+                dx = du = None
+        else:
+            y = np.empty((B, 12)); st = np.empty(B, dtype=np.int32)
+            dx = np.empty((B, 12, 12)) if grad else None
+            du = np.empty((B, 3, 12)) if grad else None
         _lib.check(_lib.lib().od_rocket_batch(self._hd, B, _dp(x), _dp(u), int(bool(proj)), _dp(y), None if dx is None else _dp(dx),
                                               None if du is None else _dp(du), _ip(st)))
         if not grad:
