@@ -40,8 +40,12 @@ inline int lanes_for(int B, bool heavy = false) {
     // planar push (20×20 reduced system, 35 variables): measured 1024 problems 5.2 / 4.1 / 3.4 ms with 4 / 8 / 16 lanes,
     // 25 600 problems 12.0 / 10.0 ms with 4 / 8 lanes (register path; shared-memory LU: 5.3 and 12.0 ms)
     if (heavy) return B <= 4096 ? 16 : 8;
-    if (B <= 2048) return 8;       // measured on B200 (hopper, r02a): 4096 problems 0.0641 ms with 4 lanes, 0.0713 with 8 (solution gathered through the mirror)
-    return 4;                      // 262144 problems: 87 M solves/s with 4 lanes (register path); 1 lane (shared-memory LU) was 57 M against 62 M before
+    // measured on B200 (hopper, r02t): 16 lanes win up to ≈ 1536 problems (every warp alone on its scheduler: the shorter per-lane chain
+    // is pure latency: 1 problem 0.0270 / 0.0332 / 0.0352 ms with 16 / 8 / 4 lanes, 512: 0.0414 / 0.0476 / 0.0536, 1536: 0.0540 / 0.0577 /
+    // 0.0567), 4 lanes from 2048 problems on (2048: 0.0557 vs 0.0576 with 16; 4096: 0.0624 / 0.0709 / 0.0987 with 4 / 8 / 16);
+    // 8 lanes are never the best choice with the solution gather through the mirror
+    if (B <= 1536) return 16;
+    return 4;                      // 262144 problems: 113 M solves/s with 4 lanes (register path)
 }
 inline bool reg_path() {
     static int v = -1;
