@@ -75,9 +75,11 @@ static inline cudaError_t launch_contact_persistent(const StepArgs& a, cudaStrea
     if (smem > 48 * 1024) {
         if ((e = cudaFuncSetAttribute(contact_sweep_kernel<M, G, PPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     }
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, contact_sweep_kernel<M, G, PPB>, G * PPB, smem);
-    if (per_sm < 1) per_sm = 1;
+    static int per_sm = 0;                                    // (per instantiation; one process drives one GPU)
+    if (!per_sm) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, contact_sweep_kernel<M, G, PPB>, G * PPB, smem);
+        if (per_sm < 1) per_sm = 1;
+    }
     int grid = sms * per_sm;
     const int need = (a.B + PPB - 1) / PPB;
     if (grid > need) grid = need;
