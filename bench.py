@@ -380,8 +380,8 @@ class Sweep:
                 self.e_st = t.empty((self.B,), dtype=t.int32).pin_memory()
                 self.dyn2 = self.od.ImplicitDynamics(self.dyn.model, self.cfg["h"], r_tol=R_TOL, κ_eval_tol=self.cfg["ke"], κ_grad_tol=self.cfg["kg"], device=self.dev.index)
                 self.e_np = (self.x_host.numpy(), self.e_out.numpy(), self.e_st.numpy())
-                return ("ImplicitDynamics.step_grad_packed -> od_step_grad_packed (pinned host buffers: inputs copied H2D, output rows written by the kernel "
-                        "straight into host memory over PCIe where the rows leave coalesced, else one D2H copy)", self.in_width * 8 * self.B, (self.out_width * 8 + 4) * self.B)
+                return ("ImplicitDynamics.step_grad_packed -> od_step_grad_packed (pinned host buffers; where the model's rows move coalesced the kernel reads its "
+                        "input rows and writes its output rows in place over PCIe, else one H2D and one D2H copy)", self.in_width * 8 * self.B, (self.out_width * 8 + 4) * self.B)
             self.sh = self.D.ShardedHostSweep(self.stepper, self.B_total, collective="fused" if self.fused is not None else "nccl")
             self.e_out = t.empty((self.B_total, self.out_width), dtype=t.float64).pin_memory()
             return ("device.ShardedHostSweep.step: pinned host shard -> H2D -> kernel + %s -> D2H of ALL gathered rows to pinned host memory on every rank" % (

@@ -337,12 +337,14 @@ static void* mapped_alias(const void* host) {
     if (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged) return at.devicePointer;
     return nullptr;
 }
-// OD_ZEROCOPY: 0 = always stage through device buffers, 1 = outputs written in place (default), 2 = inputs read in place as well.
-// Measured on B200 (hopper, 4096 problems, pinned buffers): 152 / 120 / 127 µs per call — reading the inputs over PCIe at kernel
-// start costs more than one cudaMemcpyAsync ahead of the launch.
+// OD_ZEROCOPY: 0 = always stage through device buffers, 1 = outputs written in place, 2 = inputs read in place as well (default).
+// Measured on B200 (hopper, 4096 problems, pinned buffers), µs per call: round 1 (kernel 0.098 ms, every lane loading every input
+// value) 152 / 120 / 127; round 2 (kernel 0.061 ms, the lanes of a group load their packed 80-B row once between them, whole
+// sectors) 120.0 / 98.3 / 92.6 — the cooperative row load made reading the inputs over PCIe cheaper than a cudaMemcpyAsync ahead
+// of the launch (profiles/r02v_e2e_zero_copy_modes.txt).
 static int zero_copy_mode() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("OD_ZEROCOPY"); v = e ? atoi(e) : 1; }
+    if (v < 0) { const char* e = getenv("OD_ZEROCOPY"); v = e ? atoi(e) : 2; }
     return v;
 }
 // Host-buffer entry point.  When the caller's buffers are pinned host memory (cudaHostAlloc / cudaHostRegister — what a Julia
@@ -400,8 +402,15 @@ static int step_host_rows(od_handle* hd, int B, const double* a0, const double* 
         memcpy(r + nq, q2 + (size_t)i * nq, sizeof(double) * nq);
         memcpy(r + 2 * nq, u + (size_t)i * nu, sizeof(double) * nu);
     }
-    OD_CUDA(cudaMemcpyAsync(hd->in.p, hin, in_bytes, cudaMemcpyHostToDevice, hd->stream));
-    const bool zc = want_grad && rows_leave_coalesced(hd->model, B) && zero_copy_mode() >= 1;
+    const bool coal = rows_leave_coalesced(hd->model, B);
+    const double* din = nullptr;
+    if (coal && zero_copy_mode() >= 2) {                    // the kernel reads the pinned staging rows in place (cooperative row loads)
+        OD_CUDA(cudaHostGetDevicePointer((void**)&din, hin, 0));
+    } else {
+        OD_CUDA(cudaMemcpyAsync(hd->in.p, hin, in_bytes, cudaMemcpyHostToDevice, hd->stream));
+        din = (const double*)hd->in.p;
+    }
+    const bool zc = want_grad && coal && zero_copy_mode() >= 1;
     double* dout = nullptr; int32_t* dst = nullptr;
     if (zc) {
         OD_CUDA(cudaHostGetDevicePointer((void**)&dout, hout, 0));
@@ -410,7 +419,6 @@ static int step_host_rows(od_handle* hd, int B, const double* a0, const double* 
         OD_CUDA(hd->out.reserve(out_bytes + st_bytes));
         dout = (double*)hd->out.p; dst = (int32_t*)((char*)hd->out.p + out_bytes);
     }
-    const double* din = (const double*)hd->in.p;
     StepArgs a; memset(&a, 0, sizeof(a));
     a.B = B; a.q1 = din; a.q2 = din + nq; a.u = din + 2 * nq; a.in_stride_q = (int)inw; a.in_stride_u = (int)inw; a.in_packed = 1; a.in_vel = in_vel;
     a.q3 = dout; a.dq1 = want_grad ? dout + nq : nullptr; a.dq2 = dout + nq + nq * nq; a.du = dout + nq + 2 * nq * nq;
