@@ -97,7 +97,7 @@ class Simulator:
     def step(self, q, v, u, t=1):
         """q3 = step!(sim, q, v, u, t) for one problem; the gradient simulator also refreshes `sim.grad`."""
         o = self._owner
-        q = _f64(q, (1, o.nq)); v = _f64(v, (1, o.nq)); u = _f64(np.asarray(u, dtype=np.float64)[o.idx_u1] if np.size(u) != o.nu else u, (1, o.nu))
+        q = _f64(q, (1, o.nq)); v = _f64(v, (1, o.nq)); u = _f64(u, (1, o.nu))
         q3 = np.empty((1, o.nq)); st = np.empty(1, dtype=np.int32)
         L = _lib.lib()
         if self.diff_sol:
