@@ -36,6 +36,15 @@
 // shipped build (99): measured on B200 (profiles/r02h_*), the rolled shared-memory elimination removes the instruction-cache stalls
 // and the spills but pays for it in shared-memory latency on the dependent LDS → FMA → STS chain (short-scoreboard stalls 1.0 → 2.5
 // per issue, half the wavefronts bank-conflicted): hopper 4096 0.064 → 0.107 ms, planar push 25 600 6.5 → 10.3 ms.
+// OD_SPLIT_SOC (default 1): the 3-D second-order-cone step lengths of a group are evaluated one per lane and combined by a shuffle
+// maximum instead of all of them in every lane (see ContactIP::step_length); 0 restores the replicated evaluation (A/B).
+// OD_ZSMEM_MIN_NZ (default 30: planar push only): see ContactIP::ZSM.  99 = off (A/B).
+#ifndef OD_ZSMEM_MIN_NZ
+#define OD_ZSMEM_MIN_NZ 30
+#endif
+#ifndef OD_SPLIT_SOC
+#define OD_SPLIT_SOC 1
+#endif
 #ifndef OD_LA_SMEM_MIN_NR
 #define OD_LA_SMEM_MIN_NR 99
 #endif
@@ -64,7 +73,7 @@ struct SolverOpts {           // RoboDojo InteriorPointOptions as set at referen
 };
 
 // status nibble: 0 converged, 1 iteration cap, 2 non-finite iterate or singular system
-enum : int { ST_OK = 0, ST_MAXIT = 1, ST_FAIL = 2 };
+enum : int { ST_OK = 0, ST_MAXIT = 1, ST_FAIL = 2, ST_PEND = 3 };   // ST_PEND: device-internal (parked problem of the persistent sweep), never returned
 
 // Step lengths are tracked as fractions num/den (den > 0) and compared by cross-multiplication, so that a whole step-length
 // computation costs one division instead of one per cone variable (fp64 division is ~20 instructions on the GPU).
@@ -140,7 +149,13 @@ struct ContactIP {
     // with rolled loops (GroupGJS) instead of in registers; -DOD_LA_SMEM_MIN_NR=1 builds every model that way.
     static constexpr bool LASM = REG && (NR >= OD_LA_SMEM_MIN_NR) && (PW >= NR + 1 + ((NR + 1) % 2) + 2);
     static constexpr int ROFF_PV = ((ROFF_Q3 + NQ + 1) / 2) * 2;          // pivot rows of the elimination steps (ints)
-    static constexpr int RWS0 = ROFF_PV + (LASM ? ((NR + 3) / 4) * 2 : 0);
+    // ZSM (models with NZ ≥ OD_ZSMEM_MIN_NZ: planar push): the iterate objects of the solver loop — iterate, direction, candidate and
+    // the candidate's residual, identical in all lanes of a group — live ONCE per group in the workspace instead of G times in
+    // registers / local memory (every lane stores the same value with the same warp instruction; reads are broadcasts).  Measured on
+    // B200 (profiles/r02w_*): planar push sweep 1696 → 800 bytes of stack per thread, 25 600 problems 5.52 → 5.02 ms.
+    static constexpr bool ZSM = REG && (NZ >= OD_ZSMEM_MIN_NZ);
+    static constexpr int ROFF_ZX = ((ROFF_PV + (LASM ? ((NR + 3) / 4) * 2 : 0) + 1) / 2) * 2;
+    static constexpr int RWS0 = ROFF_ZX + (ZSM ? 4 * NZ + (4 * NZ) % 2 : 0);
     static constexpr int RWS = ((RWS0 / 2) % 2 == 1) ? RWS0 : RWS0 + 2;
     static constexpr int NOUT = NQ + NQ * NTP;           // packed output row [q3 | ∂q3/∂q1 | ∂q3/∂q2 | ∂q3/∂u1]
     static_assert(!REG || NOUT <= NR * PW, "output row is staged in the matrix area");
@@ -153,6 +168,15 @@ struct ContactIP {
     static constexpr int RPL = GJ::RPL;
 
     struct Z { double q[NQ], gam[NC1], s[NC1], psi[NP1], b[NB1], spsi[NP1], sb[NB1]; };
+    // ZSM: slot `k` (0..3, NZ doubles each) of the group's shared area as an object of type T; otherwise — and always on the host,
+    // where the emulated lanes of tests/host_check.cu are free-running threads between collectives — the caller's own object
+    template <class T>
+    OD_HD static T& shared_obj(double* ws, int k, T& local) {
+#ifdef __CUDA_ARCH__
+        if constexpr (ZSM) { static_assert(sizeof(T) <= NZ * sizeof(double), "slot size"); return *reinterpret_cast<T*>(ws + ROFF_ZX + k * NZ); }
+#endif
+        return local;
+    }
     // residual in block form; bilinear rows are stored at κ = 0 (r(z;κ) only shifts rgam and rc0 by −κ)
     struct R { double d[NQ], rs[NC1], rpsi[NP1], rv[NB1], rgam[NC1], rc0[NP1], rc1[NB1]; };
     struct Lin {
@@ -562,17 +586,50 @@ struct ContactIP {
             }
         }
     }
-    OD_HD static double step_length(const Z& z, const ConeRcp& c, const Z& D, double tau) {
+    // Cones with two tangential components (3-D second-order cones; planar push: 4 contacts × primal / dual = 8 per step length):
+    // their CVXOPT step lengths are the expensive part of step_length (reciprocal square root, reciprocal, square root each) and
+    // identical in all lanes of a group.  With cooperating lanes (SPLIT_SOC) lane g evaluates candidate g, g+G, … and the group
+    // combines the maxima by shuffle — a maximum of never-NaN, non-negative values: the same number in any order.
+    __host__ __device__ static constexpr int nsoc3() { int n = 0; for (int k = 0; k < NP; ++k) if (M::cone_dim(k) == 2) ++n; return n; }
+    __host__ __device__ static constexpr int soc3_cone(int j) {
+        int n = 0, r = 0;
+        for (int k = 0; k < NP; ++k) if (M::cone_dim(k) == 2) { if (n == j) r = k; ++n; }
+        return r;
+    }
+    static constexpr bool SPLIT_SOC = OD_SPLIT_SOC && REG && G >= 4 && nsoc3() > 0 && NC > 0;
+
+    OD_HD static double step_length(const Z& z, const ConeRcp& c, const Z& D, double tau, const int g = 0, const unsigned gmask = 0xffffffffu) {
         MaxAcc rho, rho2;                                      // two independent running maxima (shorter dependent chain)
 #pragma unroll
         for (int i = 0; i < NC; ++i) { rho.add(D.gam[i] * c.gam[i]); rho2.add(D.s[i] * c.s[i]); }
+        if constexpr (SPLIT_SOC) {
+            constexpr int T = 2 * nsoc3();
+            double m = 0.0;
+#pragma unroll
+            for (int r0 = 0; r0 < T; r0 += G) {
+                // a lane without a candidate in this round keeps an interior point with a zero direction: contributes 0
+                double l0 = 1.0, l1[2] = {0.0, 0.0}, d0 = 0.0, d1[2] = {0.0, 0.0};
+#pragma unroll
+                for (int t = r0; t < ((r0 + G < T) ? r0 + G : T); ++t) {
+                    const int k = soc3_cone(t / 2), o = M::cone_off(k);
+                    if (t - r0 == g) {
+                        if (t % 2 == 0) { l0 = z.psi[k]; l1[0] = z.b[o]; l1[1] = z.b[o + 1]; d0 = D.psi[k]; d1[0] = D.b[o]; d1[1] = D.b[o + 1]; }
+                        else { l0 = z.spsi[k]; l1[0] = z.sb[o]; l1[1] = z.sb[o + 1]; d0 = D.spsi[k]; d1[0] = D.sb[o]; d1[1] = D.sb[o + 1]; }
+                    }
+                }
+                double bn = 1.0, bd = 0.0;                     // soc_step leaves (τ, den) when den > 0
+                soc_step<2>(l0, l1, d0, d1, 1.0, bn, bd);
+                m = od_max(m, bd);
+            }
+            rho2.add(Grp<G>::dmax_all(m, gmask));
+        }
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
             const int o = M::cone_off(k);
             if (M::cone_dim(k) == 1) {
                 rho.add((D.psi[k] - D.b[o]) * c.pm[k]); rho2.add((D.psi[k] + D.b[o]) * c.pp[k]);
                 rho.add((D.spsi[k] - D.sb[o]) * c.dm[k]); rho2.add((D.spsi[k] + D.sb[o]) * c.dp[k]);
-            } else {
+            } else if constexpr (!SPLIT_SOC) {
                 double bn = 1.0, bd = 0.0;                     // soc_step leaves (τ, den) when den > 0
                 soc_step<2>(z.psi[k], &z.b[o], D.psi[k], &D.b[o], 1.0, bn, bd);
                 rho.add(bd);
@@ -615,7 +672,7 @@ struct ContactIP {
             solve_carried(L, z, r, D);                           // affine direction
             ConeRcp rcp;
             cone_rcp(z, rcp);
-            const double a_aff = step_length(z, rcp, D, 1.0);
+            const double a_aff = step_length(z, rcp, D, 1.0, L.g, L.gmask);
             const double mu = cone_dot(z, D, 0.0) * (1.0 / (NCONE > 0 ? NCONE : 1));
             const double mu_aff = cone_dot(z, D, a_aff) * (1.0 / (NCONE > 0 ? NCONE : 1));
             const double ratio = od_min(od_max(0.0, mu_aff * pivot_rcp(mu)), 1.0);   // μ > 0 at any non-converged iterate
@@ -637,7 +694,7 @@ struct ContactIP {
             }
             solve(L, z, rc, D);
             const double viol = od_max(r_vio, k_vio);
-            alpha = step_length(z, rcp, D, od_max(0.95, 1.0 - viol * viol));
+            alpha = step_length(z, rcp, D, od_max(0.95, 1.0 - viol * viol), L.g, L.gmask);
         } else {
             solve_carried(L, z, r, D);                           // no cones: plain Newton direction, full step
             alpha = 1.0;
@@ -819,10 +876,9 @@ struct ContactIP {
         return rank > 0;
     }
 
-    // iterate ↔ workspace snapshot (all lanes of a group write identical values)
-    OD_HD static void store_z(const Lin& L, const Z& z) {
-        constexpr int ST = WS_STRIDE;
-        double* p = &L.ws[(REG ? ROFF_ZS : OFF_ZS) * ST];
+    // iterate ↔ flat array of NZ doubles, element e at p[e·ST] (the order of the snapshots handed to contact_ift_kernel)
+    template <int ST>
+    OD_HD static void pack_z(const Z& z, double* p) {
         int e = 0;
 #pragma unroll
         for (int i = 0; i < NQ; ++i) p[(e++) * ST] = z.q[i];
@@ -833,9 +889,8 @@ struct ContactIP {
 #pragma unroll
         for (int i = 0; i < NB; ++i) { p[(e++) * ST] = z.b[i]; p[(e++) * ST] = z.sb[i]; }
     }
-    OD_HD static void load_z(const Lin& L, Z& z) {
-        constexpr int ST = WS_STRIDE;
-        const double* p = &L.ws[(REG ? ROFF_ZS : OFF_ZS) * ST];
+    template <int ST>
+    OD_HD static void unpack_z(const double* p, Z& z) {
         int e = 0;
 #pragma unroll
         for (int i = 0; i < NQ; ++i) z.q[i] = p[(e++) * ST];
@@ -846,6 +901,9 @@ struct ContactIP {
 #pragma unroll
         for (int i = 0; i < NB; ++i) { z.b[i] = p[(e++) * ST]; z.sb[i] = p[(e++) * ST]; }
     }
+    // iterate ↔ workspace snapshot (all lanes of a group write identical values)
+    OD_HD static void store_z(const Lin& L, const Z& z) { pack_z<WS_STRIDE>(z, &L.ws[(REG ? ROFF_ZS : OFF_ZS) * WS_STRIDE]); }
+    OD_HD static void load_z(const Lin& L, Z& z) { unpack_z<WS_STRIDE>(&L.ws[(REG ? ROFF_ZS : OFF_ZS) * WS_STRIDE], z); }
 
     // initialize_z! (reference src/models/planar_push/simulator.jl:52-60 and the same pattern in the other models)
     OD_HD static void init_z(const double* q2, Z& z) {
@@ -918,6 +976,13 @@ struct StepArgs {
     // the sweep kernel to the IFT kernel.
     unsigned int* work_queue;
     double* z_snapshots;
+    // Park and resume (two launches of contact_sweep_kernel): with park_iter > 0 a problem that is still unfinished after park_iter
+    // iterations leaves the sweep — iterate to z_park (B × NZ), progress words to park_info (2 ints per problem), its index
+    // appended to park_list (counter: work_queue[1]) — so that the few problems that run to max_iter do not start their 100
+    // dependent iterations at whatever time the queue happens to reach them.  The second launch (resume = 1; queue: work_queue[2])
+    // continues all of them at once, spread over the SMs with one warp each and more lanes per problem.
+    int park_iter, resume;
+    double* z_park; int* park_list; int* park_info;
     // NVLink multicast alias of the gather buffers (torch symmetric memory multicast_ptr; null = per-peer stores): ONE multimem.st
     // per 16 bytes reaches the gather buffer of every rank — this one included — and NVSwitch does the replication.
     double* mc_out;
@@ -1006,7 +1071,12 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
     typedef ContactIP<M, G, PPB, REG> IP;
     constexpr int NQ = M::NQ, NU = M::NU;
     double th[M::NTH];
-    typename IP::Z z, D, zc;
+    typename IP::Z z_r, D_r, zc_r;
+    typename IP::R rc_r;
+    typename IP::Z& zc = IP::shared_obj(ws, 0, zc_r);        // ZSM models: one copy per group in the workspace (see ContactIP::ZSM)
+    typename IP::R& rc = IP::shared_obj(ws, 1, rc_r);
+    typename IP::Z& D = IP::shared_obj(ws, 2, D_r);
+    typename IP::Z& z = IP::shared_obj(ws, 3, z_r);
     {
         const long long ig = a.eta ? a.eta_i0 + i : i;
         const int src = a.eta ? (int)(ig / (a.n_eta + 1)) : i;
@@ -1068,7 +1138,7 @@ OD_HD void contact_step_one(const StepArgs& a, const int i, double* ws, const in
     int it = 0, ls = 0, it_e = 0, it_g = 0, st_e = 0, st_g = 0;
     for (;;) {
         // ---- candidate z − αΔ and its residual (the only residual call site) ----------------------------------------------
-        typename IP::R rc; double rv2, kv2;
+        double rv2, kv2;
 #if OD_INPLACE_Z
         // Prepared variant: the iterate is advanced in place, z ← z − step·Δ, and a rejected step is taken back by the
         // difference of the step lengths — no second copy of the iterate, no copy on acceptance.  Identical arithmetic on the
@@ -1360,7 +1430,12 @@ __global__ void __launch_bounds__(G * PPB) contact_sweep_kernel(const StepArgs a
     const unsigned full = 0xffffffffu;
     double* ws = od_smem + slot * IP::WS_SLOT;
     double th[M::NTH];
-    typename IP::Z z, D, zc;
+    typename IP::Z z_r, D_r, zc_r;
+    typename IP::R rc_r;
+    typename IP::Z& zc = IP::shared_obj(ws, 0, zc_r);
+    typename IP::R& rc = IP::shared_obj(ws, 1, rc_r);
+    typename IP::Z& D = IP::shared_obj(ws, 2, D_r);
+    typename IP::Z& z = IP::shared_obj(ws, 3, z_r);
     typename IP::Lin L;
     L.ws = ws; L.g = g; L.gmask = full; L.ok = true;
     double trc[IP::NTC1], trv[IP::NTV1];
@@ -1385,23 +1460,36 @@ __global__ void __launch_bounds__(G * PPB) contact_sweep_kernel(const StepArgs a
         }
         active = false; have = false;
     };
+    unsigned int* const queue = a.resume ? a.work_queue + 2 : a.work_queue;
+    // resume: the parked problems of the previous launch (their count is final)
+    const int bound = a.resume ? (int)*reinterpret_cast<volatile unsigned int*>(a.work_queue + 1) : a.B;
     for (;;) {
         // ---- groups without a problem claim the next index
         int claim = -1;
-        if (!have && g == 0) claim = (int)atomicAdd(a.work_queue, 1u);
+        if (!have && g == 0) claim = (int)atomicAdd(queue, 1u);
         claim = __shfl_sync(full, claim, lane & ~(G - 1));
-        if (!have && claim >= 0 && claim < a.B) {
-            i = claim;
+        if (!have && claim >= 0 && claim < bound) {
+            i = a.resume ? a.park_list[claim] : claim;
             double q2v[NQ];
             load_problem_plain<M>(a, i, th, q2v);
             IP::init_z(q2v, z);
             M::trig_const(th, trc);
-            D = z; alpha = 0.0; r_vio = 0.0; k_vio = 0.0;
+            alpha = 0.0; r_vio = 0.0; k_vio = 0.0;
             first = true; eval_done = !a.want_eval; grad_done = !a.want_grad; active = true; have = true;
             it = 0; ls = 0; it_e = 0; it_g = 0; st_e = 0; st_g = 0;
+            if (a.resume) {
+                // the parked iterate re-enters as a "first" candidate (z − 0·Δ: its residual is evaluated, it is accepted without a
+                // line-search test and without counting an iteration) with the progress words of the first launch
+                IP::template unpack_z<1>(a.z_park + (size_t)i * IP::NZ, z);
+                const int sw = a.park_info[2 * i], iw = a.park_info[2 * i + 1];
+                st_e = sw & 15; st_g = (sw >> 4) & 15; it_e = iw & 0xffff; it_g = (iw >> 16) & 0xffff;
+                eval_done = st_e != ST_PEND; grad_done = st_g != ST_PEND;
+                it = eval_done ? it_g : it_e;
+            }
+            D = z;
         }
         // ---- candidate z − αΔ and its residual
-        typename IP::R rc; double rv2 = 0.0, kv2 = 0.0;
+        double rv2 = 0.0, kv2 = 0.0;
         bool retry = false;
         if (warp_any(active)) {
             IP::candidate(z, D, alpha, zc);
@@ -1413,7 +1501,7 @@ __global__ void __launch_bounds__(G * PPB) contact_sweep_kernel(const StepArgs a
         if (block_or(retry)) continue;
         // ---- accepted iterate: termination tests (a group's lanes agree on every one of these; the warp's groups may not: the
         // snapshot's group barriers are warp barriers, so it is taken by whole warps with the other groups masked)
-        bool take_snapshot = false, done_now = false;
+        bool take_snapshot = false, done_now = false, park = false;
         if (active) {
             z = zc; r_vio = rv2; k_vio = kv2;
             if (!first) ++it;
@@ -1436,20 +1524,31 @@ __global__ void __launch_bounds__(G * PPB) contact_sweep_kernel(const StepArgs a
                 take_snapshot = true;
             }
             done_now = bad || capped || (eval_done && grad_done);
+            park = !done_now && a.park_iter > 0 && it >= a.park_iter;
         }
-        if (warp_any(take_snapshot)) {
+        if (warp_any(take_snapshot || park)) {
             IP::store_z(L, z);                                  // (groups that are not taking one rewrite their own workspace: harmless)
             L.sync();
             if (take_snapshot) {
                 double* dst = a.z_snapshots + (size_t)i * IP::NZ;
                 for (int e = g; e < IP::NZ; e += G) dst[e] = ws[IP::ROFF_ZS + e];
             }
+            if (park) {
+                double* dst = a.z_park + (size_t)i * IP::NZ;
+                for (int e = g; e < IP::NZ; e += G) dst[e] = ws[IP::ROFF_ZS + e];
+                if (g == 0) {
+                    a.park_info[2 * i] = (eval_done ? st_e : ST_PEND) | ((grad_done ? st_g : ST_PEND) << 4);
+                    a.park_info[2 * i + 1] = (eval_done ? it_e : it) | ((grad_done ? it_g : it) << 16);
+                    a.park_list[atomicAdd(a.work_queue + 1, 1u)] = i;
+                }
+            }
             L.sync();
         }
         if (done_now) finish();
+        if (park) { active = false; have = false; }
         // ---- anything left for this block?  (a group without a problem will claim one at the top if the queue still has any)
         bool more = false;
-        if (!have && g == 0) more = *reinterpret_cast<volatile unsigned int*>(a.work_queue) < (unsigned)a.B;
+        if (!have && g == 0) more = *reinterpret_cast<volatile unsigned int*>(queue) < (unsigned)bound;
         if (!block_or(active || more)) break;
         if (!warp_any(active)) continue;
         // ---- Newton system at z, direction, step length
@@ -1563,7 +1662,7 @@ OD_HD void contact_rollout_one(const RolloutArgs& ra, const int r, double* ws, c
     for (int k = 0; k < 4; ++k) a.fric[k] = ra.fric[k];
     a.want_eval = 1; a.want_grad = 0; a.eta = nullptr; a.n_eta = 0; a.eta_i0 = 0;
     a.n_peers = 0; a.self_rank = 0; a.gather_row0 = 0; a.gather_width = 0;
-    a.packed_out = 0; a.in_packed = 0; a.in_vel = 0; a.sync_counter = nullptr; a.sync_epoch = 0; a.sync_epoch_dev = nullptr; a.mc_out = nullptr; a.mc_flags = nullptr; a.work_queue = nullptr; a.z_snapshots = nullptr;
+    a.packed_out = 0; a.in_packed = 0; a.in_vel = 0; a.sync_counter = nullptr; a.sync_epoch = 0; a.sync_epoch_dev = nullptr; a.mc_out = nullptr; a.mc_flags = nullptr; a.work_queue = nullptr; a.z_snapshots = nullptr; a.park_iter = 0; a.resume = 0; a.z_park = nullptr; a.park_list = nullptr; a.park_info = nullptr;
     a.opts = ra.opts;
     const double alpha = ra.alpha ? ra.alpha[r] : 1.0;
     const double* ub = ra.ubar + (size_t)r * ra.ubar_stride;

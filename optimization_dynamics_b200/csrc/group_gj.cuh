@@ -86,6 +86,17 @@ template <int G> struct Grp {
             }
 #endif
     }
+    // largest value over the lanes of the group (values are never NaN where this is used), replicated in every lane
+    OD_HD static double dmax_all(double v, unsigned m) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+        for (int d = 1; d < G; d <<= 1) { const double o = __shfl_xor_sync(m, v, d, G); v = o > v ? o : v; }
+#else
+        if (HostLaneTeam* t = host_lane_team())
+            for (int d = 1; d < G; d <<= 1) { const double o = t->shfl_f64(v, t->lane ^ d); v = o > v ? o : v; }
+#endif
+        return v;
+    }
     OD_HD static unsigned umax_all(unsigned v, unsigned m) {
 #ifdef __CUDA_ARCH__
 #pragma unroll

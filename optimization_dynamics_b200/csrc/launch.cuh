@@ -64,13 +64,24 @@ inline int persist_min_batch() {
     if (v < 0) { const char* e = getenv("OD_PERSIST"); v = e ? atoi(e) : 1; if (v == 1) v = 4096; }
     return v;
 }
+// OD_PARK_ITER (default 16; 0 = off): problems of the persistent sweep that are unfinished after this many iterations are parked and
+// continued by a second launch — all of them at once, one warp per block, 16 lanes per problem (StepArgs::park_iter).
+inline int park_iter_default() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("OD_PARK_ITER"); v = e ? atoi(e) : 16; if (v < 0) v = 0; }
+    return v;
+}
 template <class M, int G, int PPB>
-static inline cudaError_t launch_contact_persistent(const StepArgs& a, cudaStream_t s) {
+static inline cudaError_t launch_contact_persistent(const StepArgs& a0, cudaStream_t s) {
+    StepArgs a = a0;
+    a.resume = 0;
+    a.park_iter = (a.z_park && a.park_list && a.park_info && park_iter_default() < a.opts.max_iter) ? park_iter_default() : 0;
     typedef ContactIP<M, G, PPB, true> IP;
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
     constexpr size_t smem = sizeof(double) * PPB * IP::WS;
-    cudaError_t e = cudaMemsetAsync(a.work_queue, 0, sizeof(unsigned int), s);
+    static_assert(smem <= 227 * 1024, "sweep kernel: shared memory per block");
+    cudaError_t e = cudaMemsetAsync(a.work_queue, 0, 4 * sizeof(unsigned int), s);   // [sweep queue, parked count, resume queue, -]
     if (e != cudaSuccess) return e;
     if (smem > 48 * 1024) {
         if ((e = cudaFuncSetAttribute(contact_sweep_kernel<M, G, PPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
@@ -86,6 +97,20 @@ static inline cudaError_t launch_contact_persistent(const StepArgs& a, cudaStrea
     contact_sweep_kernel<M, G, PPB><<<grid, G * PPB, smem, s>>>(a);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     last_launch_kernels() = 1;
+    if (a.park_iter > 0) {
+        typedef ContactIP<M, 16, 2, true> IPR;
+        constexpr size_t smem_r = sizeof(double) * 2 * IPR::WS;
+        if (smem_r > 48 * 1024) {
+            if ((e = cudaFuncSetAttribute(contact_sweep_kernel<M, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r)) != cudaSuccess) return e;
+        }
+        StepArgs b = a;
+        b.park_iter = 0; b.resume = 1;
+        int grid_r = sms * 4;                                 // the parked count is only known on the device: blocks without work leave at once
+        if (grid_r > (a.B + 1) / 2) grid_r = (a.B + 1) / 2;
+        contact_sweep_kernel<M, 16, 2><<<grid_r, 32, smem_r, s>>>(b);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        last_launch_kernels() = 2;
+    }
     if (a.want_grad && a.dq1) {
         constexpr int PPB2 = 32 / G;                          // one warp per block: the IFT kernel is short and phased by construction
         constexpr size_t smem2 = sizeof(double) * PPB2 * ContactIP<M, G, PPB2, true>::WS;
@@ -94,7 +119,7 @@ static inline cudaError_t launch_contact_persistent(const StepArgs& a, cudaStrea
         }
         contact_ift_kernel<M, G, PPB2><<<(a.B + PPB2 - 1) / PPB2, G * PPB2, smem2, s>>>(a);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        last_launch_kernels() = 2;
+        last_launch_kernels() += 1;
     }
     return cudaSuccess;
 }

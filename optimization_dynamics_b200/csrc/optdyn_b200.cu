@@ -215,9 +215,14 @@ static int launch_step(od_handle* hd, StepArgs& a, bool grad_sim_q3 = false) {
     if (grad_sim_q3) a.opts.kappa_eval_tol = hd->opts.kappa_grad_tol;
     if (hd->model == OD_PLANAR_PUSH && a.n_peers <= 1) {         // scratch of the persistent sweep (launch.cuh decides whether it is used)
         Dims d; dims_of(hd->model, &d);
-        if (hd->sweep.reserve(256 + sizeof(double) * (size_t)d.nz * a.B) == cudaSuccess) {
-            a.work_queue = (unsigned int*)hd->sweep.p;
-            a.z_snapshots = (double*)((char*)hd->sweep.p + 256);
+        const size_t zb = sizeof(double) * (size_t)d.nz * a.B;   // [counters | snapshots | parked iterates | parked progress words | parked list]
+        if (hd->sweep.reserve(256 + 2 * zb + 3 * sizeof(int) * (size_t)a.B) == cudaSuccess) {
+            char* base = (char*)hd->sweep.p;
+            a.work_queue = (unsigned int*)base;
+            a.z_snapshots = (double*)(base + 256);
+            a.z_park = (double*)(base + 256 + zb);
+            a.park_info = (int*)(base + 256 + 2 * zb);
+            a.park_list = a.park_info + 2 * (size_t)a.B;
         }
     }
     cudaError_t e;
