@@ -141,7 +141,11 @@ struct ContactIP {
     // row), iterate snapshot, q3.  Even pitch and offsets: rows are moved as 16-byte pairs; WS/2 odd spreads problems over banks.
     // Models with the rank-revealing IFT run it (once per problem) in the shared-memory-LU layout at the start of the same
     // workspace, so the snapshot / q3 slots sit behind both areas.
-    static constexpr int PW = ((NR + NTP + 1) / 2) * 2;
+    // Row pitch: even (16-byte pairs) with PW/2 odd — the lanes of a group move their own rows r, r+1, … as 16-byte accesses, and a
+    // pitch of 4 (mod 8) words puts 8 consecutive rows on disjoint banks.  (Planar push had 32 doubles = 256 bytes: every row on the
+    // same banks, 59 % of its shared-memory wavefronts were bank-conflict replays, profiles/r02x_planar_push_sweep_and_resume.json.)
+    static constexpr int PW0 = ((NR + NTP + 1) / 2) * 2;
+    static constexpr int PW = ((PW0 / 2) % 2 == 1) ? PW0 : PW0 + 2;
     static constexpr int ROBUST_END = M::ROBUST_IFT ? OFF_CP + NR : 0;
     static constexpr int ROFF_ZS = ((((NR * PW > ROBUST_END) ? NR * PW : ROBUST_END) + 1) / 2) * 2;
     static constexpr int ROFF_Q3 = ROFF_ZS + NZ;
