@@ -271,6 +271,9 @@ class Sweep:
             self.stepper = D.DeviceStepper(self.dyn)
             self.in_width, self.out_width = self.stepper.in_width, self.stepper.out_width
             self.kernel = "od::contact_step_kernel<%s> (cooperative lanes, register Gauss-Jordan)" % cfg["model"]
+            if cfg["model"] == "planarpush":
+                self.kernel = ("od::contact_sweep_kernel<planarpush, 8 lanes> (persistent, block-phased, queue-fed) + its resume launch for the problems parked "
+                               "at 16 iterations (32 lanes) + od::contact_ift_kernel (rank-revealing IFT); per-warp od::contact_step_kernel below 4096 problems per GPU")
             if kind == "bundle":
                 self.gb = od.GradientBundle(model, eta=od.workloads.bundle_perturbations(self.in_width, N=cfg["N"], eps=1e-4, seed=0))
                 self.bundle = D.DeviceBundle(self.stepper, self.gb)

@@ -987,6 +987,10 @@ struct StepArgs {
     // continues all of them at once, spread over the SMs with one warp each and more lanes per problem.
     int park_iter, resume;
     double* z_park; int* park_list; int* park_info;
+    // HOST side only (never read by a kernel): a second stream and two events of the handle.  When present, the resume launch and the IFT
+    // of the problems that finished in the sweep run side by side (fork after the sweep, join before the IFT of the parked problems) —
+    // ≈ 1 % of a batch is parked, but it has 84 dependent iterations left: a millisecond during which the SMs would otherwise idle.
+    void* side_stream; void* ev_fork; void* ev_join;
     // NVLink multicast alias of the gather buffers (torch symmetric memory multicast_ptr; null = per-peer stores): ONE multimem.st
     // per 16 bytes reaches the gather buffer of every rank — this one included — and NVSwitch does the replication.
     double* mc_out;
@@ -1424,7 +1428,7 @@ __global__ void __launch_bounds__(G * PPB, OD_MIN_BLOCKS) contact_step_kernel(co
 // differentiates all problems afterwards.  Per problem the arithmetic is that of contact_step_one, operation for operation: the
 // results are bit-identical (tests/test_gpu_parity.py).
 template <class M, int G, int PPB>
-__global__ void __launch_bounds__(G * PPB) contact_sweep_kernel(const StepArgs a) {
+__device__ __forceinline__ void contact_sweep_body(const StepArgs& a) {
 #ifdef __CUDA_ARCH__
     typedef ContactIP<M, G, PPB, true> IP;
     constexpr int NQ = M::NQ;
@@ -1580,36 +1584,55 @@ __global__ void __launch_bounds__(G * PPB) contact_sweep_kernel(const StepArgs a
 #endif
 }
 
-// IFT at the snapshots of contact_sweep_kernel: one group per problem, ordinary grid.  Writes the Jacobian blocks and folds a failed
-// factorisation into the gradient nibble of the status word.
 template <class M, int G, int PPB>
-__global__ void __launch_bounds__(G * PPB) contact_ift_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(G * PPB) contact_sweep_kernel(const StepArgs a) { contact_sweep_body<M, G, PPB>(a); }
+
+// IFT at the snapshots of contact_sweep_kernel: one group per problem.  Writes the Jacobian blocks and folds a failed factorisation
+// into the gradient nibble of the status word.  MODE 0: problems block·PPB + slot of an ordinary grid.  MODE 1: the same, but a
+// PARKED problem (park_info word non-zero; its snapshot and status are still being produced by the resume launch running beside this
+// one) is only walked through — the group must keep its warp's barriers — at the initial iterate, and its status is left alone; its
+// rows are written again, from the real snapshot, by the MODE 2 launch that follows: the parked list, any grid, whole blocks striding.
+template <class M, int G, int PPB, int MODE>
+__device__ __forceinline__ void contact_ift_body(const StepArgs& a, const int block, const int nblocks) {
 #ifdef __CUDA_ARCH__
     typedef ContactIP<M, G, PPB, true> IP;
     constexpr int NQ = M::NQ;
     static_assert(M::ROBUST_IFT, "the persistent sweep is instantiated for the models with the rank-revealing IFT");
     extern __shared__ __align__(16) double od_smem[];
     const int slot = threadIdx.x / G, g = threadIdx.x % G;
-    int i = blockIdx.x * PPB + slot;
-    if (i >= a.B) i = a.B - 1;
     double* ws = od_smem + slot * IP::WS_SLOT;
     typename IP::Lin L;
     L.ws = ws; L.g = g; L.gmask = 0xffffffffu; L.ok = true;
-    double th[M::NTH], q2v[NQ], trc[IP::NTC1], trv[IP::NTV1];
-    load_problem_plain<M>(a, i, th, q2v);
-    M::trig_const(th, trc);
-    const double* src = a.z_snapshots + (size_t)i * IP::NZ;
-    for (int e = g; e < IP::NZ; e += G) ws[IP::ROFF_ZS + e] = src[e];
-    L.sync();
-    typename IP::Z z;
-    IP::load_z(L, z);
-    M::trig_var(z.q, th, trv);
-    IP::assemble(z, th, trc, trv, L);
-    const bool ok = IP::sensitivities_robust(L, z, th, trc, trv, a.dq1 + (size_t)i * a.out_stride_dq, a.dq2 + (size_t)i * a.out_stride_dq,
-                                             a.du + (size_t)i * a.out_stride_du);
-    if (!ok && g == 0 && a.status) a.status[i] = (a.status[i] & 15) | (ST_FAIL << 4);
+    const int count = (MODE == 2) ? (int)*reinterpret_cast<volatile unsigned int*>(a.work_queue + 1) : a.B;
+    for (int c0 = block * PPB; c0 < count; c0 += nblocks * PPB) {          // (MODE 0 / 1: one trip)
+        int c = c0 + slot;
+        if (c >= count) c = count - 1;
+        const int i = (MODE == 2) ? a.park_list[c] : c;
+        const bool dry = (MODE == 1) && a.park_info[2 * i] != 0;
+        double th[M::NTH], q2v[NQ], trc[IP::NTC1], trv[IP::NTV1];
+        load_problem_plain<M>(a, i, th, q2v);
+        M::trig_const(th, trc);
+        const double* src = a.z_snapshots + (size_t)i * IP::NZ;
+        typename IP::Z z;
+        if (dry) {
+            IP::init_z(q2v, z);
+            IP::store_z(L, z);
+        } else {
+            for (int e = g; e < IP::NZ; e += G) ws[IP::ROFF_ZS + e] = src[e];
+        }
+        L.sync();
+        IP::load_z(L, z);
+        M::trig_var(z.q, th, trv);
+        IP::assemble(z, th, trc, trv, L);
+        const bool ok = IP::sensitivities_robust(L, z, th, trc, trv, a.dq1 + (size_t)i * a.out_stride_dq, a.dq2 + (size_t)i * a.out_stride_dq,
+                                                 a.du + (size_t)i * a.out_stride_du);
+        if (!ok && !dry && g == 0 && a.status) a.status[i] = (a.status[i] & 15) | (ST_FAIL << 4);
+        L.sync();
+    }
 #endif
 }
+template <class M, int G, int PPB, int MODE>
+__global__ void __launch_bounds__(G * PPB) contact_ift_kernel(const StepArgs a) { contact_ift_body<M, G, PPB, MODE>(a, blockIdx.x, gridDim.x); }
 
 // A rank whose shard is empty still has to take part in the fused cross-GPU barrier: publish the epoch, wait for the peers.
 static __global__ void gather_sync_only_kernel(const StepArgs a) {
@@ -1666,7 +1689,7 @@ OD_HD void contact_rollout_one(const RolloutArgs& ra, const int r, double* ws, c
     for (int k = 0; k < 4; ++k) a.fric[k] = ra.fric[k];
     a.want_eval = 1; a.want_grad = 0; a.eta = nullptr; a.n_eta = 0; a.eta_i0 = 0;
     a.n_peers = 0; a.self_rank = 0; a.gather_row0 = 0; a.gather_width = 0;
-    a.packed_out = 0; a.in_packed = 0; a.in_vel = 0; a.sync_counter = nullptr; a.sync_epoch = 0; a.sync_epoch_dev = nullptr; a.mc_out = nullptr; a.mc_flags = nullptr; a.work_queue = nullptr; a.z_snapshots = nullptr; a.park_iter = 0; a.resume = 0; a.z_park = nullptr; a.park_list = nullptr; a.park_info = nullptr;
+    a.packed_out = 0; a.in_packed = 0; a.in_vel = 0; a.sync_counter = nullptr; a.sync_epoch = 0; a.sync_epoch_dev = nullptr; a.mc_out = nullptr; a.mc_flags = nullptr; a.work_queue = nullptr; a.z_snapshots = nullptr; a.park_iter = 0; a.resume = 0; a.z_park = nullptr; a.park_list = nullptr; a.park_info = nullptr; a.side_stream = nullptr; a.ev_fork = nullptr; a.ev_join = nullptr;
     a.opts = ra.opts;
     const double alpha = ra.alpha ? ra.alpha[r] : 1.0;
     const double* ub = ra.ubar + (size_t)r * ra.ubar_stride;

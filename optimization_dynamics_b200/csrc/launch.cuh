@@ -57,11 +57,12 @@ inline bool reg_path() {
 inline int& last_launch_kernels() { static thread_local int n = 1; return n; }
 
 // OD_PERSIST (default 1): persistent block-phased sweep + separate IFT kernel for the models with the rank-revealing IFT, from
-// this many problems on (1 = default threshold 4096, 0 = never, n = from n problems).  Needs the scratch the C ABI layer provides
-// (work_queue, z_snapshots) and no fused gather.
+// this many problems on (1 = default threshold 3072, 0 = never, n = from n problems; measured, profiles/r02za_*: 2048 problems 1.26 ms
+// per-warp kernel / 1.31 ms sweep, 3072: 1.44 / 1.36, 4096: 1.52 / 1.33).  Needs the scratch the C ABI layer provides (work_queue,
+// z_snapshots) and no fused gather.
 inline int persist_min_batch() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("OD_PERSIST"); v = e ? atoi(e) : 1; if (v == 1) v = 4096; }
+    if (v < 0) { const char* e = getenv("OD_PERSIST"); v = e ? atoi(e) : 1; if (v == 1) v = 3072; }
     return v;
 }
 // OD_PARK_ITER (default 16; 0 = off): problems of the persistent sweep that are unfinished after this many iterations are parked and
@@ -70,6 +71,12 @@ inline int park_iter_default() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("OD_PARK_ITER"); v = e ? atoi(e) : 16; if (v < 0) v = 0; }
     return v;
+}
+// OD_TAIL_OVERLAP (default 1): resume of the parked problems and IFT of the finished ones side by side on two streams; 0 = one after the other
+inline bool tail_overlap() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("OD_TAIL_OVERLAP"); v = e ? atoi(e) : 1; }
+    return v != 0;
 }
 template <class M, int G, int PPB>
 static inline cudaError_t launch_contact_persistent(const StepArgs& a0, cudaStream_t s) {
@@ -94,32 +101,65 @@ static inline cudaError_t launch_contact_persistent(const StepArgs& a0, cudaStre
     int grid = sms * per_sm;
     const int need = (a.B + PPB - 1) / PPB;
     if (grid > need) grid = need;
+    const bool grad = a.want_grad && a.dq1;
+    if (a.park_iter > 0 && grad) {                            // progress words double as the "parked" marks of the IFT role below
+        if ((e = cudaMemsetAsync(a.park_info, 0, 2 * sizeof(int) * (size_t)a.B, s)) != cudaSuccess) return e;
+    }
     contact_sweep_kernel<M, G, PPB><<<grid, G * PPB, smem, s>>>(a);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     last_launch_kernels() = 1;
+    constexpr int PPB2 = 32 / G;                              // IFT: one warp per block — short, and phased by construction
+    constexpr size_t smem2 = sizeof(double) * PPB2 * ContactIP<M, G, PPB2, true>::WS;
+    const int ift_blocks = (a.B + PPB2 - 1) / PPB2;
     if (a.park_iter > 0) {
-        typedef ContactIP<M, 16, 2, true> IPR;
-        constexpr size_t smem_r = sizeof(double) * 2 * IPR::WS;
-        if (smem_r > 48 * 1024) {
-            if ((e = cudaFuncSetAttribute(contact_sweep_kernel<M, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r)) != cudaSuccess) return e;
-        }
+        // resume: a whole warp per parked problem (32 lanes: one matrix row per lane; loop 5866 instructions against 6648 with 16
+        // lanes), up to 8 one-warp blocks per SM; blocks without work leave at once — the parked count is only known on the device
+        constexpr int RG = 32, RPPB = 1;
+        constexpr size_t smem_r = sizeof(double) * RPPB * ContactIP<M, RG, RPPB, true>::WS;
         StepArgs b = a;
         b.park_iter = 0; b.resume = 1;
-        int grid_r = sms * 4;                                 // the parked count is only known on the device: blocks without work leave at once
-        if (grid_r > (a.B + 1) / 2) grid_r = (a.B + 1) / 2;
-        contact_sweep_kernel<M, 16, 2><<<grid_r, 32, smem_r, s>>>(b);
+        int grid_r = sms * 8;
+        if (grid_r > a.B) grid_r = a.B;
+        if (smem_r > 48 * 1024) {
+            if ((e = cudaFuncSetAttribute(contact_sweep_kernel<M, RG, RPPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r)) != cudaSuccess) return e;
+        }
+        if (grad && smem2 > 48 * 1024) {
+            if ((e = cudaFuncSetAttribute(contact_ift_kernel<M, G, PPB2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)) != cudaSuccess) return e;
+            if ((e = cudaFuncSetAttribute(contact_ift_kernel<M, G, PPB2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)) != cudaSuccess) return e;
+            if ((e = cudaFuncSetAttribute(contact_ift_kernel<M, G, PPB2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)) != cudaSuccess) return e;
+        }
+        if (grad && a.side_stream && a.ev_fork && a.ev_join && tail_overlap()) {
+            // fork: the resume launch stays on the caller's stream, the IFT of everything that finished in the sweep runs beside it on
+            // the handle's second stream (parked problems are walked through dry); join; then the IFT of the parked problems
+            cudaStream_t side = (cudaStream_t)a.side_stream;
+            if ((e = cudaEventRecord((cudaEvent_t)a.ev_fork, s)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(side, (cudaEvent_t)a.ev_fork, 0)) != cudaSuccess) return e;
+            contact_sweep_kernel<M, RG, RPPB><<<grid_r, RG * RPPB, smem_r, s>>>(b);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            contact_ift_kernel<M, G, PPB2, 1><<<ift_blocks, G * PPB2, smem2, side>>>(b);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            if ((e = cudaEventRecord((cudaEvent_t)a.ev_join, side)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(s, (cudaEvent_t)a.ev_join, 0)) != cudaSuccess) return e;
+            contact_ift_kernel<M, G, PPB2, 2><<<(sms < ift_blocks ? sms : ift_blocks), G * PPB2, smem2, s>>>(b);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            last_launch_kernels() = 4;
+        } else {
+            contact_sweep_kernel<M, RG, RPPB><<<grid_r, RG * RPPB, smem_r, s>>>(b);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            last_launch_kernels() = 2;
+            if (grad) {                                       // no second stream (or OD_TAIL_OVERLAP=0): resume, then the IFT of all problems
+                contact_ift_kernel<M, G, PPB2, 0><<<ift_blocks, G * PPB2, smem2, s>>>(a);
+                if ((e = cudaGetLastError()) != cudaSuccess) return e;
+                last_launch_kernels() = 3;
+            }
+        }
+    } else if (grad) {
+        if (smem2 > 48 * 1024) {
+            if ((e = cudaFuncSetAttribute(contact_ift_kernel<M, G, PPB2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)) != cudaSuccess) return e;
+        }
+        contact_ift_kernel<M, G, PPB2, 0><<<ift_blocks, G * PPB2, smem2, s>>>(a);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         last_launch_kernels() = 2;
-    }
-    if (a.want_grad && a.dq1) {
-        constexpr int PPB2 = 32 / G;                          // one warp per block: the IFT kernel is short and phased by construction
-        constexpr size_t smem2 = sizeof(double) * PPB2 * ContactIP<M, G, PPB2, true>::WS;
-        if (smem2 > 48 * 1024) {
-            if ((e = cudaFuncSetAttribute(contact_ift_kernel<M, G, PPB2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)) != cudaSuccess) return e;
-        }
-        contact_ift_kernel<M, G, PPB2><<<(a.B + PPB2 - 1) / PPB2, G * PPB2, smem2, s>>>(a);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        last_launch_kernels() += 1;
     }
     return cudaSuccess;
 }
@@ -133,7 +173,7 @@ static inline cudaError_t launch_contact(const StepArgs& a, cudaStream_t s) {
         if (reg_path()) {
             if constexpr (WIDE && M::ROBUST_IFT) {
                 if (persist_min_batch() > 0 && a.B >= persist_min_batch() && a.n_peers <= 1 && a.work_queue && (!a.want_grad || !a.dq1 || a.z_snapshots)) {
-                    if (lanes == 16) return launch_contact_persistent<M, 16, 16>(a, s);
+                    // 8 lanes at every size (measured, r02z: 4096 problems 1.37 ms against 1.64 with 16 lanes, 25 600: 3.05 / 4.05)
                     return launch_contact_persistent<M, 8, 32>(a, s);
                 }
                 // a gather with peers keeps one-warp blocks (the fused barrier counts blocks as they finish; rows should leave early)

@@ -100,6 +100,7 @@ struct od_handle {
     od_options opts;
     double params[4];
     cudaStream_t stream; bool own_stream;
+    cudaStream_t side; cudaEvent_t ev_fork, ev_join;   // planar push: second stream of the persistent sweep's tail (launch.cuh), else null
     DevBuf in, out, st, aux, aux2, sweep;      // sweep: work queue + iterate snapshots of the persistent sweep (planar push)
     PinBuf hin, hout;
     int64_t launches;
@@ -165,6 +166,16 @@ od_handle* od_create(int model, double h, const od_options* opts, const double* 
     for (int k = 0; k < nparams && k < 4 && params; ++k) hd->params[k] = params[k];
     if ((e = cudaStreamCreateWithFlags(&hd->stream, cudaStreamNonBlocking)) != cudaSuccess) { fail("cudaStreamCreate", e); delete hd; return nullptr; }
     hd->own_stream = true;
+    hd->side = nullptr; hd->ev_fork = nullptr; hd->ev_join = nullptr;
+    if (model == OD_PLANAR_PUSH) {                            // optional: without them the tail of the sweep runs on one stream
+        if (cudaStreamCreateWithFlags(&hd->side, cudaStreamNonBlocking) != cudaSuccess) hd->side = nullptr;
+        if (hd->side && (cudaEventCreateWithFlags(&hd->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                         cudaEventCreateWithFlags(&hd->ev_join, cudaEventDisableTiming) != cudaSuccess)) {
+            if (hd->ev_fork) cudaEventDestroy(hd->ev_fork);
+            cudaStreamDestroy(hd->side); hd->side = nullptr; hd->ev_fork = nullptr; hd->ev_join = nullptr;
+            cudaGetLastError();
+        }
+    }
     return hd;
 }
 
@@ -174,6 +185,7 @@ void od_destroy(od_handle* hd) {
     cudaStreamSynchronize(hd->stream);
     hd->in.release(); hd->out.release(); hd->st.release(); hd->aux.release(); hd->aux2.release(); hd->sweep.release();
     hd->hin.release(); hd->hout.release();
+    if (hd->side) { cudaStreamSynchronize(hd->side); cudaEventDestroy(hd->ev_fork); cudaEventDestroy(hd->ev_join); cudaStreamDestroy(hd->side); }
     if (hd->own_stream) cudaStreamDestroy(hd->stream);
     delete hd;
 }
@@ -224,6 +236,7 @@ static int launch_step(od_handle* hd, StepArgs& a, bool grad_sim_q3 = false) {
             a.park_info = (int*)(base + 256 + 2 * zb);
             a.park_list = a.park_info + 2 * (size_t)a.B;
         }
+        a.side_stream = hd->side; a.ev_fork = hd->ev_fork; a.ev_join = hd->ev_join;
     }
     cudaError_t e;
     switch (hd->model) {
@@ -270,6 +283,22 @@ int od_step_grad_packed_device(od_handle* hd, int B, const double* in, double* o
     return launch_step(hd, a);
 }
 
+}  // extern "C"
+
+// Rows [row0, row0 + B) of this rank's gather buffer → the same rows of every peer's buffer (peer-mapped stores over NVLink).  Used
+// where the kernels do not forward their rows themselves: the persistent sweep of the planar push.
+static __global__ void gather_forward_kernel(const StepArgs a) {
+    const size_t n = (size_t)a.B * a.gather_width, off = (size_t)a.gather_row0 * a.gather_width;
+    const double* src = a.peer_out[a.self_rank] + off;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        const double v = src[k];
+        for (int p = 0; p < a.n_peers; ++p)
+            if (p != a.self_rank) a.peer_out[p][off + k] = v;
+    }
+}
+
+extern "C" {
+
 // Multi-GPU derivative sweep, every variant (see od_gather_desc in the header)
 int od_step_grad_packed_gather_ex_device(od_handle* hd, int B, const double* in, const od_gather_desc* g, int32_t* status, int32_t* iters) {
     if (!hd) return fail("null handle");
@@ -309,6 +338,21 @@ int od_step_grad_packed_gather_ex_device(od_handle* hd, int B, const double* in,
         gather_sync_only_kernel<<<1, 32, 0, hd->stream>>>(a);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail("gather_sync_only_kernel launch", e);
+        hd->launches++;
+        return 0;
+    }
+    if (hd->model == OD_PLANAR_PUSH && !sync && !a.mc_out && g->world > 1 && reg_path() && persist_min_batch() > 0 && B >= persist_min_batch()) {
+        // large shard of the planar push: the persistent sweep (launch.cuh) writes this rank's rows into its own gather buffer, one
+        // copy kernel forwards them to the peers; the caller's barrier follows as after the per-warp kernel
+        StepArgs local = a;
+        local.n_peers = 1;
+        const int rc = launch_step(hd, local);
+        if (rc != 0) return rc;
+        int blocks = (int)(((size_t)B * outw + 255) / 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        gather_forward_kernel<<<blocks, 256, 0, hd->stream>>>(a);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail("gather_forward_kernel launch", e);
         hd->launches++;
         return 0;
     }

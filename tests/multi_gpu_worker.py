@@ -30,7 +30,7 @@ def main():
         return dyn, D.DeviceStepper(dyn), gen, h
 
     # ---- fused gather: even / ragged / fewer-problems-than-ranks shards, every barrier + store variant, register and non-register models
-    for name, sizes in (("hopper", (4096, 1001, 1)), ("cartpole_friction", (513,)), ("planar_push", (130,))):
+    for name, sizes in (("hopper", (4096, 1001, 1)), ("cartpole_friction", (513,)), ("planar_push", (130, 6600))):   # 6600: shards of ≥ 3072 run the persistent sweep + one forwarding kernel
         dyn, st, gen, h = make(name)
         for B_total in sizes:
             q1, q2, u = gen(B_total, h=h, seed=5)
