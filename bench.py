@@ -306,6 +306,9 @@ class Sweep:
                     self.collective = ("all-gather fused into the kernel: each finished row leaves as %s; %s" % (
                         how, "cross-rank barrier fused as well (one system fence per block, flags published by the last block, device-side epoch)"
                         if self.fused.sync == "kernel" else "symmetric-memory barrier launch after the kernel"))
+                    if cfg["model"] == "planarpush" and self.B >= 3072:
+                        self.collective = ("persistent sweep into this rank's rows of its own gather buffer, one forwarding kernel stores them into every peer's "
+                                           "buffer over NVLink (P2P), symmetric-memory barrier launch")
                 else:
                     self.collective = "kernel + ncclAllGather of the packed rows"
         elif kind == "bundle":
