@@ -42,6 +42,10 @@
 #ifndef OD_ZSMEM_MIN_NZ
 #define OD_ZSMEM_MIN_NZ 30
 #endif
+// OD_PITCH_G4 (default 1): row pitch rule of the 4-lane configurations (see ContactIP::PW); 0 = the PW/2-odd rule for every G (A/B).
+#ifndef OD_PITCH_G4
+#define OD_PITCH_G4 1
+#endif
 #ifndef OD_SPLIT_SOC
 #define OD_SPLIT_SOC 1
 #endif
@@ -144,8 +148,11 @@ struct ContactIP {
     // Row pitch: even (16-byte pairs) with PW/2 odd — the lanes of a group move their own rows r, r+1, … as 16-byte accesses, and a
     // pitch of 4 (mod 8) words puts 8 consecutive rows on disjoint banks.  (Planar push had 32 doubles = 256 bytes: every row on the
     // same banks, 59 % of its shared-memory wavefronts were bank-conflict replays, profiles/r02x_planar_push_sweep_and_resume.json.)
+    // With 4 lanes per problem a quarter-warp (one 16-byte wavefront) holds TWO groups: rows 24 (mod 32) words apart take the even
+    // 4-bank units and the neighbouring problem (workspaces 4 mod 8 words apart) the odd ones — PW ≡ 12 (mod 16): hopper 28 (22 gave
+    // a 2-way conflict on every row move: 1.6 M of the hopper kernel's 5.9 M shared-memory wavefronts), cartpole 12, acrobot 12.
     static constexpr int PW0 = ((NR + NTP + 1) / 2) * 2;
-    static constexpr int PW = ((PW0 / 2) % 2 == 1) ? PW0 : PW0 + 2;
+    static constexpr int PW = (G <= 4 && OD_PITCH_G4) ? PW0 + ((12 - PW0 % 16) + 16) % 16 : ((PW0 / 2) % 2 == 1) ? PW0 : PW0 + 2;
     static constexpr int ROBUST_END = M::ROBUST_IFT ? OFF_CP + NR : 0;
     static constexpr int ROFF_ZS = ((((NR * PW > ROBUST_END) ? NR * PW : ROBUST_END) + 1) / 2) * 2;
     static constexpr int ROFF_Q3 = ROFF_ZS + NZ;
