@@ -47,6 +47,14 @@ inline int lanes_for(int B, bool heavy = false) {
     if (B <= 1536) return 16;
     return 4;                      // 262144 problems: 113 M solves/s with 4 lanes (register path)
 }
+#ifndef OD_BUILD_PHASED_4LANE
+#define OD_BUILD_PHASED_4LANE 0
+#endif
+inline int phased_min_batch() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("OD_PHASED"); v = e ? atoi(e) : 0; }
+    return v;
+}
 inline bool reg_path() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("OD_REG"); v = e ? atoi(e) : 1; }
@@ -179,6 +187,13 @@ static inline cudaError_t launch_contact(const StepArgs& a, cudaStream_t s) {
                 // a gather with peers keeps one-warp blocks (the fused barrier counts blocks as they finish; rows should leave early)
                 if (bsync_min_batch() > 0 && a.B >= bsync_min_batch() && lanes == 8 && a.n_peers <= 1) return launch_contact_cfg<M, 8, 32, true, true>(a, s);
             }
+#if OD_BUILD_PHASED_4LANE
+            // A/B (rejected, profiles/r02ze_*): the 4-lane hopper kernel in block-phased 128-thread blocks — shared instruction fetches, but
+            // the votes become barriers: 4096 problems 0.0586 -> 0.0771 ms, 262 144: 2.28 -> 2.47 ms.  -DOD_BUILD_PHASED_4LANE=1 + OD_PHASED=n.
+            if constexpr (WIDE && !M::ROBUST_IFT) {
+                if (lanes == 4 && phased_min_batch() > 0 && a.B >= phased_min_batch() && a.n_peers <= 1) return launch_contact_cfg<M, 4, 32, true, true>(a, s);
+            }
+#endif
             if constexpr (WIDE) { if (lanes == 16) return launch_contact_cfg<M, 16, 2, true>(a, s); }
             if constexpr (WIDE) { if (lanes == 8) return launch_contact_cfg<M, 8, 4, true>(a, s); }
             if (lanes >= 4) return launch_contact_cfg<M, 4, 8, true>(a, s);
