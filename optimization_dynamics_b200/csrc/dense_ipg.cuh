@@ -14,7 +14,9 @@ template <class M, int G>
 struct DenseIPG {
     static constexpr int NZ = M::NZ, NTH = M::NTH, NTHP = M::NTHP;
     static constexpr int NCONE = M::NORT + M::NSOC;
-    static constexpr int PW = ((NZ + NTHP + 1) / 2) * 2;        // staging pitch: [rz | rθ' or the Newton right-hand side]
+    // staging pitch: [rz | rθ' or the Newton right-hand side]; bank rule of ContactIP::PW (4 lanes: ≡ 12 mod 16 — dynamics 28 already, projection 14 → 28)
+    static constexpr int PW0 = ((NZ + NTHP + 1) / 2) * 2;
+    static constexpr int PW = (G <= 4) ? PW0 + ((12 - PW0 % 16) + 16) % 16 : ((PW0 / 2) % 2 == 1) ? PW0 : PW0 + 2;
     static constexpr int WS = NZ * PW;                           // staging doubles per problem
     typedef GroupGJ<NZ, NZ + 1, G> GJ;
     typedef GroupGJ<NZ, NZ + NTHP, G> GJS;
