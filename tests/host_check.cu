@@ -283,3 +283,22 @@ extern "C" int hc_sincos(int n, const double* x, double* s, double* c) {
     for (int i = 0; i < n; ++i) od_sincos(x[i], s + i, c + i);
     return 0;
 }
+
+// Shared-memory layout of the register path for one (model, lanes) configuration: out = {NR, PW (row pitch, doubles), workspace doubles
+// per problem, rows per lane} — tests/test_host_logic.py replays the row moves of a quarter-warp against the 32 banks.
+template <class M, int G>
+static void layout_t(int* out) { typedef ContactIP<M, G, 32 / G, true> IP; out[0] = IP::NR; out[1] = IP::PW; out[2] = IP::WS_SLOT; out[3] = IP::RPL; }
+extern "C" int hc_layout(int model, int lanes, int* out) {
+    switch (model * 100 + lanes) {
+        case 4: layout_t<AcrobotImpactModel, 4>(out); return 0;
+        case 204: layout_t<CartpoleFrictionModel, 4>(out); return 0;
+        case 404: layout_t<PlanarPushModel, 4>(out); return 0;
+        case 408: layout_t<PlanarPushModel, 8>(out); return 0;
+        case 416: layout_t<PlanarPushModel, 16>(out); return 0;
+        case 432: layout_t<PlanarPushModel, 32>(out); return 0;
+        case 504: layout_t<HopperModel, 4>(out); return 0;
+        case 508: layout_t<HopperModel, 8>(out); return 0;
+        case 516: layout_t<HopperModel, 16>(out); return 0;
+    }
+    return 1;
+}

@@ -138,3 +138,10 @@ def sincos(x):
     s = np.empty_like(x); c = np.empty_like(x)
     assert lib().hc_sincos(x.size, _p(x), _p(s), _p(c)) == 0
     return s, c
+
+
+def layout(model, lanes):
+    """(NR, row pitch PW in doubles, workspace doubles per problem, rows per lane) of the register path for one configuration."""
+    out = (C.c_int * 4)()
+    assert lib().hc_layout(MODELS[model], int(lanes), out) == 0
+    return tuple(out)

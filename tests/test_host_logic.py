@@ -430,3 +430,28 @@ def test_bundle_prepare_inverts_the_normal_matrix_and_reports_singularity(built)
     assert L.od_bundle_prepare(ncol, N, eta.ctypes.data_as(_lib.c_double_p), hinv.ctypes.data_as(_lib.c_double_p)) != 0
     assert b"singular" in L.od_last_error()
     assert L.od_bundle_prepare(17, N, eta.ctypes.data_as(_lib.c_double_p), hinv.ctypes.data_as(_lib.c_double_p)) != 0     # 2nq+nu > 16 unsupported
+
+
+@pytest.mark.parametrize("name,lanes", [("hopper", 4), ("hopper", 8), ("hopper", 16), ("cartpole_friction", 4), ("acrobot_impact", 4),
+                                         ("planar_push", 8), ("planar_push", 16), ("planar_push", 32)])
+def test_row_moves_of_the_register_path_are_bank_conflict_free(name, lanes):
+    """The lanes of a group move their own matrix rows between registers and the shared-memory mirror as 16-byte words
+    (group_gj.cuh: factor_v2, fetch_rows); one wavefront serves a quarter-warp (8 lanes x 16 bytes = the 32 banks).  Replays those
+    accesses for every shipped (model, lanes) configuration against the bank map: with the row pitch / workspace size rules of
+    ContactIP::PW each quarter-warp must need exactly ONE wavefront.  (Planar push used to sit at a 256-byte pitch — every row on
+    the same four banks, 59 % of the kernel's shared-memory wavefronts were replays; hopper 4 lanes at 2-way conflicts.)"""
+    NR, PW, WS, RPL = H.layout(name, lanes)
+    assert PW % 2 == 0 and WS % 2 == 0
+    for s in range(RPL):
+        for j in (0, 2, PW - 2):
+            for q0 in range(0, 32, 8):                       # a quarter-warp
+                per_bank = {}
+                for lane in range(q0, q0 + 8):
+                    slot, g = divmod(lane, lanes)
+                    r = s * lanes + g
+                    if r >= NR:
+                        continue                             # padding rows are not moved
+                    word = 2 * (slot * WS + r * PW + j)      # 4-byte words; a lane touches 4 consecutive banks
+                    for w in range(4):
+                        per_bank.setdefault((word + w) % 32, set()).add((word + w) // 32)
+                assert all(len(v) == 1 for v in per_bank.values()), (name, lanes, PW, WS, s, j, q0)
