@@ -61,7 +61,7 @@ inline bool reg_path() {
     return v != 0;
 }
 
-// Kernels launched by the last launch_contact call of this thread (the persistent sweep is two kernels): od_launch_count bookkeeping.
+// Kernels launched by the last launch_contact call of this thread (the persistent sweep is two to four kernels: sweep, resume, IFT of the finished, IFT of the parked): od_launch_count bookkeeping.
 inline int& last_launch_kernels() { static thread_local int n = 1; return n; }
 
 // OD_PERSIST (default 1): persistent block-phased sweep + separate IFT kernel for the models with the rank-revealing IFT, from
