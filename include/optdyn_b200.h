@@ -118,7 +118,10 @@ int od_step_grad_packed_gather_sync_device(od_handle* hd, int B, const double* i
  *   epoch / epoch_dev: epoch >= 1 = the host supplies the step's epoch;  epoch == 0 = the epoch lives in *epoch_dev (a zeroed uint64
  *                      in this rank's device memory), advanced by one per launch on the device — such launches can sit in a CUDA
  *                      graph and be replayed (every rank must replay the same launches).
- *   An empty shard (B == 0) with the fused barrier still publishes / waits, so ragged splits and B_total < world do not hang. */
+ *   An empty shard (B == 0) with the fused barrier still publishes / waits, so ragged splits and B_total < world do not hang.
+ *   Planar push (rank-revealing IFT; peer stores without the fused barrier only): shards of at least OD_PERSIST (default 3072)
+ *   problems run the persistent sweep into this rank's own rows, then ONE forwarding kernel stores those rows into every peer's
+ *   buffer; smaller shards forward each row from the step kernel.  Either way the caller's barrier follows. */
 typedef struct od_gather_desc {
     int32_t world, rank;
     int64_t row0;
