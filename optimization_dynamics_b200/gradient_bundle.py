@@ -28,7 +28,25 @@ class GradientBundle:
                 eta[i, rng.integers(0, self.nz)] = eps * rng.normal()
         self.eta = np.ascontiguousarray(eta, dtype=np.float64).reshape(-1, self.nz)
         self.N = self.eta.shape[0]
+        self.eps = eps
         self.dz = np.zeros((self.ny, self.nz))
+
+    def unsampled(self):
+        """Coordinates of [q1; q2; u1] that no perturbation touches: the fit's normal matrix Σ ηηᵀ is singular in them (the reference
+        draws the N coordinates at random once, src/gradient_bundle.jl:49-54, and then fails in its LU; here the fit reports it)."""
+        return np.flatnonzero(~(self.eta != 0.0).any(axis=0))
+
+    def resample(self, rng=None, cover=True):
+        """Draw the N one-hot perturbations again (same law as the constructor).  cover=True (needs N ≥ nz): the first nz draws take
+        the coordinates 0 … nz−1 once each, so every column of the Jacobian is determined."""
+        rng = np.random.default_rng() if rng is None else rng
+        eta = np.zeros((self.N, self.nz))
+        for i in range(self.N):
+            j = i if (cover and self.N >= self.nz and i < self.nz) else rng.integers(0, self.nz)
+            w = self.eps * rng.normal()
+            eta[i, j] = w if w != 0.0 else self.eps
+        self.eta = eta
+        return self
 
 
 def gradient_batch(im_dyn, gb, q1, q2, u):

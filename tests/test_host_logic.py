@@ -455,3 +455,19 @@ def test_row_moves_of_the_register_path_are_bank_conflict_free(name, lanes):
                     for w in range(4):
                         per_bank.setdefault((word + w) % 32, set()).add((word + w) // 32)
                 assert all(len(v) == 1 for v in per_bank.values()), (name, lanes, PW, WS, s, j, q0)
+
+
+def test_gradient_bundle_resampling_covers_every_coordinate():
+    """GradientBundle(model; N, ϵ) draws N one-hot perturbations at random once (reference src/gradient_bundle.jl:49-54); with N not much
+    larger than nz some coordinate is often never drawn and the reference's fit is singular.  unsampled() names those coordinates,
+    resample(cover=True) redraws with every coordinate taken at least once."""
+    import optimization_dynamics_b200 as od
+    rng = np.random.default_rng(0)
+    gb = od.GradientBundle(od.cartpole_friction, N=6, ϵ=1e-4, rng=rng)          # nz = 5: six random draws rarely cover all five
+    assert gb.eta.shape == (6, 5) and ((gb.eta != 0).sum(1) == 1).all()
+    gb.eta[:, 3] = 0.0
+    assert 3 in gb.unsampled()
+    gb.resample(rng=rng)
+    assert gb.unsampled().size == 0 and ((gb.eta != 0).sum(1) == 1).all() and np.abs(gb.eta).max() < 1e-3
+    few = od.GradientBundle(od.cartpole_friction, N=3, ϵ=1e-4, rng=rng).resample(rng=rng)     # N < nz: cannot cover, law unchanged
+    assert few.eta.shape == (3, 5) and few.unsampled().size >= 2
