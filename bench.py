@@ -262,7 +262,7 @@ class Sweep:
             self.info = od.RocketInfo(od.rocket, 12.5, cfg["h"], device=dev.index)
             self.rk = D.DeviceRocket(self.info)
             self.in_width, self.out_width = 15, 12 + 144 + 36
-            self.kernel = "od::rocket_kernel_g<lanes=8> (SOC projection 10x10 + implicit midpoint 12x12, register Gauss-Jordan)"
+            self.kernel = "od::rocket_kernel_g<4 lanes, 128-thread blocks phased at the phase boundaries> (SOC projection 10x10 + implicit midpoint 12x12, register Gauss-Jordan; 8 lanes below ~2000 problems)"
         else:
             model = getattr(od, cfg["model"])
             if cfg["fric"] is not None:

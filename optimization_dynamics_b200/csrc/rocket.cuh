@@ -77,6 +77,12 @@ __global__ void __launch_bounds__(BLOCK) rocket_kernel(const RocketArgs a) {
 
 // ---- cooperative-lane version (latency configuration): G lanes per problem, register Gauss–Jordan, warp-synchronous ------------
 // Shared-memory workspace per problem: staging rows of the larger system, then the IFT results DZ (12×15) and DPROJ (3×3).
+template <bool PHASED>
+OD_HD void phase_barrier() {
+#ifdef __CUDA_ARCH__
+    if (PHASED) __syncthreads();          // (conditions around the call sites are uniform over the block: launch arguments only)
+#endif
+}
 template <int G>
 struct RocketG {
     typedef DenseIPG<RocketProjModel, G> P;
@@ -85,6 +91,10 @@ struct RocketG {
     static constexpr int O_DZ = STAGE, O_DP = O_DZ + 12 * 15, WS0 = ((O_DP + 9 + 1) / 2) * 2;
     static constexpr int WS = ((WS0 / 2) % 2 == 1) ? WS0 : WS0 + 2;
 
+    // PHASED (blocks of several warps): a block barrier at each phase boundary — projection loop | its IFT | dynamics loop | its
+    // IFT.  The kernel is 143 KB of mostly straight-line code that every warp walks once per problem (ncu: 2.2 stall cycles per
+    // issue waiting for instructions, profiles/r02zj_*); warps that enter a phase together share its instruction fetches.
+    template <bool PHASED = false>
     OD_HD static void run(const RocketArgs& a, const int i, double* ws, const int g) {
         double ue[3];
         int st_p = 0, it_p = 0, st_d = 0, it_d = 0;
@@ -101,6 +111,7 @@ struct RocketG {
             st_p = P::solve(c, zp, thp, a.opts.r_tol, a.opts.kappa_eval_tol, a.opts.max_iter, a.opts.max_ls, a.opts.ls_scale, &it_p);
 #pragma unroll
             for (int k = 0; k < 3; ++k) ue[k] = zp[k];
+            phase_barrier<PHASED>();
             if (a.want_grad) {
                 if (!P::template sensitivities<3>(c, zp, thp, DP) && st_p != ST_FAIL) st_p = ST_FAIL;
                 P::sync();
@@ -108,6 +119,7 @@ struct RocketG {
             if (a.uproj && g == 0) for (int k = 0; k < 3; ++k) a.uproj[(size_t)i * 3 + k] = ue[k];
             if (a.duproj && a.want_grad) for (int k = g; k < 9; k += G) a.duproj[(size_t)i * 9 + k] = DP[k];
         }
+        phase_barrier<PHASED>();
         if (!a.proj_only) {
             typename Dy::Ctx c{ws, g, 0xffffffffu};
             double z[12], th[16];
@@ -119,6 +131,7 @@ struct RocketG {
 #pragma unroll
                 for (int k = 0; k < 12; ++k) if (G == 1 || k % G == g) a.y[(size_t)i * 12 + k] = z[k];
             }
+            phase_barrier<PHASED>();
             if (a.want_grad) {
                 if (!Dy::template sensitivities<12>(c, z, th, DZ) && st_d != ST_FAIL) st_d = ST_FAIL;
                 Dy::sync();
@@ -141,14 +154,14 @@ struct RocketG {
     }
 };
 
-template <int G, int PPB>
+template <int G, int PPB, bool PHASED = false>
 __global__ void __launch_bounds__(G * PPB) rocket_kernel_g(const RocketArgs a) {
     extern __shared__ __align__(16) double od_smem[];
     static_assert((G * PPB) % 32 == 0, "whole warps: the solve runs warp-synchronously");
     const int slot = threadIdx.x / G, g = threadIdx.x % G;
     int i = blockIdx.x * PPB + slot;
     if (i >= a.B) i = a.B - 1;               // padding lanes repeat the last problem (identical values, same addresses)
-    RocketG<G>::run(a, i, od_smem + slot * RocketG<G>::WS, g);
+    RocketG<G>::template run<PHASED>(a, i, od_smem + slot * RocketG<G>::WS, g);
 }
 
 }  // namespace od

@@ -168,6 +168,29 @@ def test_rocket_matches_oracle(od, O, proj):
     assert np.abs(yg - gold["y"])[okg].max() <= Q3_TOL and np.abs(dxg - gold["dx"].transpose(0, 2, 1))[okg].max() <= GRAD_TOL
 
 
+@pytest.mark.parametrize("proj", [False, True])
+def test_rocket_at_the_benchmark_batch_matches_oracle_and_the_small_batch_kernel(od, O, proj):
+    """BASELINE.json configs[4] is 8192 rocket problems: that size runs the 4-lane kernel (with the projection: phased 128-thread
+    blocks with a barrier at each phase boundary, csrc/rocket.cuh), 1024 problems the 8-lane one.  Both against the oracle by the usual
+    rule, and against each other on the first 1024 problems (same arithmetic per problem, whatever the lane count, up to contraction)."""
+    B = 8192
+    x, u = od.workloads.rocket_batch(B, seed=4)
+    info = od.RocketInfo(od.rocket, 12.5, 0.05)
+    y, dx, du, st = info.step_batch(x, u, proj)
+    o = O.rocket_batch(x, u, 0.05, 12.5, proj, True)
+    ok = (o["status"] == 0) & (st == 0) & (o["margin"] > 1e-6)
+    assert ok.mean() > 0.9
+    assert np.abs(y - o["y"])[ok].max() <= Q3_TOL
+    assert np.abs(dx - o["dx"].transpose(0, 2, 1))[ok].max() <= GRAD_TOL and np.abs(du - o["du"].transpose(0, 2, 1))[ok].max() <= GRAD_TOL
+    assert (st == o["status"]).mean() >= 0.999
+    ys, dxs, dus, sts = info.step_batch(x[:1024], u[:1024], proj)
+    assert (sts == st[:1024]).mean() >= 0.999
+    both = (sts == 0) & (st[:1024] == 0)
+    dy = np.abs(ys - y[:1024])[both].max(); dj = max(np.abs(dxs - dx[:1024])[both].max(), np.abs(dus - du[:1024])[both].max())
+    print("rocket proj=%s: 4-lane (8192-problem launch) vs 8-lane (1024-problem launch) kernel on the same problems: max |dy| %.1e, max |dJ| %.1e" % (proj, dy, dj))
+    assert dy <= 1e-10 and dj <= 1e-8          # separately compiled instantiations: multiply-add contraction may differ
+
+
 def test_device_resident_packed_path_and_launch_accounting(od):
     import torch
     from optimization_dynamics_b200.device import DeviceStepper
