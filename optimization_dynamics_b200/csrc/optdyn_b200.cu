@@ -745,12 +745,28 @@ int od_bundle_batch(od_handle* hd, int B, int N, const double* eta, const double
     return 0;
 }
 
-// OD_ROCKET_PHASED (default 4): 4-lane rocket kernel with the projection in phased 128-thread blocks; 1 = one-warp blocks, no barriers
+// OD_ROCKET_PHASED (default 4): 4-lane rocket kernel with the projection in phased blocks of 2 / 3 / 4 warps; 1 = one-warp blocks, no barriers
 static int rocket_phased_warps() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("OD_ROCKET_PHASED"); v = e ? atoi(e) : 4; }
     return v;
 }
+
+}  // extern "C"
+
+template <int PPB>
+static cudaError_t launch_rocket_phased(const RocketArgs& a, cudaStream_t s) {
+    constexpr int G = 4;
+    constexpr size_t smem = sizeof(double) * PPB * RocketG<G>::WS;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(rocket_kernel_g<G, PPB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    rocket_kernel_g<G, PPB, true><<<(a.B + PPB - 1) / PPB, G * PPB, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+extern "C" {
 
 static int launch_rocket(od_handle* hd, RocketArgs& a) {
     if (hd->model != OD_ROCKET) return fail("rocket entry point needs an OD_ROCKET handle");
@@ -767,10 +783,9 @@ static int launch_rocket(od_handle* hd, RocketArgs& a) {
     } else if (reg_path() && lanes >= 4 && a.proj && rocket_phased_warps() > 1) {
         // with the projection: 128-thread blocks with a barrier at each phase boundary (rocket.cuh: PHASED) — measured on B200, 8192
         // problems (profiles/r02zl_*): 0.166 -> 0.132 ms; without the projection the one-warp blocks stay (0.0437 vs 0.0478 ms)
-        constexpr int G = 4, PPB = 32;
-        constexpr size_t smem = sizeof(double) * PPB * RocketG<G>::WS;
-        if (smem > 48 * 1024) OD_CUDA(cudaFuncSetAttribute(rocket_kernel_g<G, PPB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rocket_kernel_g<G, PPB, true><<<(a.B + PPB - 1) / PPB, G * PPB, smem, hd->stream>>>(a);
+        const int w = rocket_phased_warps();
+        cudaError_t e = (w == 2) ? launch_rocket_phased<16>(a, hd->stream) : (w == 3) ? launch_rocket_phased<24>(a, hd->stream) : launch_rocket_phased<32>(a, hd->stream);
+        if (e != cudaSuccess) return fail("rocket_kernel_g (phased) launch", e);
     } else if (reg_path() && lanes >= 4) {
         constexpr int G = 4, PPB = 8;
         rocket_kernel_g<G, PPB><<<(a.B + PPB - 1) / PPB, G * PPB, sizeof(double) * PPB * RocketG<G>::WS, hd->stream>>>(a);
